@@ -1,0 +1,141 @@
+/*
+ * mis.h -- C-ABI of the B200-native meshless inflatable soft-body step.
+ *
+ * The reference (Megumi-X/meshless-inflatable-softbody) has no plugin / FFI
+ * interface: its hot path is a set of module-level NVIDIA-Warp kernels launched
+ * from a Python script.  This header is the boundary a replacement shared
+ * library provides; every entry point cites the reference code it replaces.
+ * The reference-side binding a maintainer would add is a ctypes stub, shown in
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.
+ *   - `stream` is a cudaStream_t passed as void* (0 = the legacy default stream).
+ *     Work is enqueued on it; no entry point synchronises the host unless its
+ *     comment says so.
+ *   - Pointers named *_dev are device pointers, *_host are host pointers (pinned
+ *     for true asynchrony).  Per-particle arrays are in the CALLER's particle
+ *     order (the order of x0 given to mis_create); the library keeps its own
+ *     cell-sorted structure-of-arrays copies and un-permutes on export.
+ *   - vec3 arrays are n*3 floats (AoS, as wp.array(dtype=vec3)); mat33 arrays are
+ *     n*9 floats row-major (as wp.array(dtype=mat33)).
+ *   - Return value: 0 = ok, negative = error (MIS_E_*); mis_last_error() gives a
+ *     message for the calling thread.
+ *   - One MisSim per stream, not re-entrant; distinct sims are independent.
+ */
+#ifndef MIS_H_
+#define MIS_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIS_OK              0
+#define MIS_E_INVALID      -1   /* bad argument                                   */
+#define MIS_E_CUDA         -2   /* a CUDA runtime call failed                     */
+#define MIS_E_STATE        -3   /* call order violated (e.g. step before startup) */
+#define MIS_E_UNSUPPORTED  -4   /* size/feature outside what this build supports  */
+
+typedef struct MisSim MisSim;
+
+/* Scene constants: the module-level constants of sim.py captured into its kernels. */
+typedef struct MisParams {
+    float h;                 /* sim.py:25   kernel radius, support 2h               */
+    float damping;           /* sim.py:26                                           */
+    float dt;                /* sim.py:65   time_step                               */
+    float k_col;             /* sim.py:68   collision_penalty_stiffness             */
+    float col_range;         /* sim.py:69   collision_range                         */
+    float stiff_a, stiff_b;  /* sim.py:215  stress factor = a - b*ratio (200, 199)  */
+    float tanh_k;            /* sim.py:110  ratio = 0.5*tanh(k*x)+0.5 (3)           */
+    int   grid_x, grid_y, grid_z; /* sim.py:123-125 wp.HashGrid dims (cell_index export only) */
+    /* sim_taichi.py deltas, 0 = sim.py behaviour */
+    int   symmetric_pair;    /* sim_taichi.py:157  f_ij uses F_j                    */
+    int   identity_rot;      /* sim_taichi.py:129  R = I                            */
+    int   self_density;      /* sim_taichi.py:97   rho includes j == i              */
+    int   euler;             /* sim_taichi.py:167-172 symplectic Euler              */
+    int   no_contact;        /* sim_taichi.py has no ground penalty                 */
+    /* tuning (0 = library default) */
+    int   lanes_per_particle;/* 8, 16 or 32 lanes cooperate on one particle         */
+    int   keep_fields;       /* 1: also store A_pq each step (diagnostics export)   */
+    int   graph_steps;       /* steps per captured CUDA graph chunk (0 = default)   */
+} MisParams;
+
+typedef struct MisNeighborInfo {
+    long long total_pairs;   /* sum of neighbour counts (directed pairs)            */
+    int   max_neighbors;
+    int   n;
+    int   cell_min[3];       /* integer cell coordinate of the grid origin          */
+    int   cell_dim[3];       /* dense cell table dims (x fastest)                   */
+    float cell_width;        /* 2h                                                  */
+} MisNeighborInfo;
+
+const char* mis_last_error(void);
+/* library / build identification, e.g. "mis_b200 sm_100a <date>" */
+const char* mis_version(void);
+
+/* Replaces the allocation block sim.py:72-95 + wp.from_numpy(points_np) sim.py:85.
+ * x0_dev: n*3 fp32 reference positions.  Copies x0; the caller keeps ownership.  */
+int mis_create(int n, const float* x0_dev, const MisParams* params, void* stream, MisSim** out);
+int mis_destroy(MisSim* sim);
+
+/* Replaces wp.HashGrid(...).build(init_position, 2h), sim.py:123-127: cell binning of x0
+ * (radix sort on Morton keys of the integer cell coordinates, dense cell table) plus the
+ * static neighbour lists {j != i : |x0_i - x0_j|/h < 2} that the reference re-discovers
+ * in every hash_grid_query (sim.py:161,178,203,224).  Synchronises the host (it sizes
+ * the lists).  Idempotent: queries are centred on x0, so a rebuild yields identical
+ * structures.  Called by mis_create; callable again to time the rebuild.            */
+int mis_build_neighbors(MisSim* sim, void* stream);
+int mis_get_neighbor_info(MisSim* sim, MisNeighborInfo* out);
+/* Bit-exact checks against the reference structures.  Any pointer may be NULL.
+ *   cell_index_dev[n]   : wp.HashGrid linear cell index of each particle (caller order)
+ *   cell_coords_dev[3n] : integer cell coordinates int(p / cell_width) (caller order)
+ *   perm_dev[n]         : caller id of the particle in sorted slot s (cell-sorted order,
+ *                         ascending caller id inside a cell = hash_grid_point_id)     */
+int mis_export_cells(MisSim* sim, int* cell_index_dev, int* cell_coords_dev, int* perm_dev, void* stream);
+/* dense cell table over cell_dim (x fastest): sorted-slot range [start, end) per cell */
+int mis_export_cell_ranges(MisSim* sim, int* start_dev, int* end_dev, void* stream);
+/* CSR neighbour lists in caller ids: offsets_dev[n+1] (row = caller id), nbr_dev[total_pairs]
+ * (row entries in the library's walk order; compare as sets).                        */
+int mis_export_neighbors(MisSim* sim, long long* offsets_dev, int* nbr_dev, void* stream);
+
+/* --- control functions, sim.py:279-308.  Arrays are per particle, caller order. --- */
+/* set_mass (sim.py:306-308): stores m and re-runs compute_v_i (sim.py:154-167).      */
+int mis_set_mass(MisSim* sim, const float* mass_dev, void* stream);
+/* set_youngs_modulus + set_poisson_ratio (sim.py:288-300): mu, lam from E, nu.       */
+int mis_set_material(MisSim* sim, const float* youngs_dev, const float* poisson_dev, void* stream);
+/* x -> ratio = 0.5*tanh(k x)+0.5, compute_ratio sim.py:107-110.                      */
+int mis_set_design(MisSim* sim, const float* x_dev, void* stream);
+/* external_forces array, sim.py:94,279-283 (n*3).                                    */
+int mis_set_ext_force(MisSim* sim, const float* f_dev, void* stream);
+int mis_set_ext_force_host(MisSim* sim, const float* f_host, void* stream);
+/* free_points mask, sim.py:81,285-286 (n*3, component-wise multiplier).              */
+int mis_set_dirichlet(MisSim* sim, const float* free_dev, void* stream);
+
+/* startup kernel sim.py:261-266 (x = x0, v = v0) + the frame-0 force evaluation
+ * sim.py:349-351.                                                                   */
+int mis_startup(MisSim* sim, const float v0[3], void* stream);
+/* resume from an arbitrary frame (x, v): re-primes the elastic force at x.           */
+int mis_set_state(MisSim* sim, const float* x_dev, const float* v_dev, void* stream);
+/* n_steps iterations of the loop body sim.py:352-358
+ * (part_1 -> compute_A_pq -> compute_nabla_u -> compute_elastic_forces -> part_2).   */
+int mis_step(MisSim* sim, int n_steps, void* stream);
+/* position[f], velocity[f] of the current frame (sim.py:334,368-369), caller order.  */
+int mis_get_state(MisSim* sim, float* x_dev, float* v_dev, void* stream);
+int mis_get_state_host(MisSim* sim, float* x_host, float* v_host, void* stream);
+/* Per-particle fields of the current frame, caller order; any pointer may be NULL.
+ * A_pq (needs keep_fields), R = U V^T, def_grad, S = compute_sigma, elastic force,
+ * rho, volume  (sim.py:154-235).                                                    */
+int mis_get_fields(MisSim* sim, float* A_dev, float* R_dev, float* F_dev, float* S_dev,
+                   float* fel_dev, float* rho_dev, float* vol_dev, void* stream);
+/* Evaluate the elastic force at an arbitrary configuration x (n*3) without touching the
+ * state: compute_A_pq -> compute_nabla_u -> compute_elastic_forces once.              */
+int mis_eval_forces(MisSim* sim, const float* x_dev, float* fel_dev, void* stream);
+/* number of kernels this sim has launched so far (bench.py's gpu_launches)           */
+long long mis_launch_count(MisSim* sim);
+/* device time of the most recent mis_step split per kernel family is taken by the
+ * caller with CUDA events; these return the kernel names for reports.               */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIS_H_ */

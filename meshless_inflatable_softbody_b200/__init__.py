@@ -2,14 +2,20 @@
 
 Host side is Python/PyTorch (device memory, streams, torch.distributed); all particle
 arithmetic runs in hand-written sm_100a CUDA kernels behind the C-ABI of include/mis.h.
-There is no CPU fallback: importing the simulator without the built library fails loudly.
+There is no CPU fallback: constructing a Simulator without a CUDA device or without the
+built library fails loudly.
 """
+import importlib
+
 from .config import SceneConfig  # noqa: F401
 from . import scenes  # noqa: F401
 
+__all__ = ["SceneConfig", "scenes", "Simulator", "native"]
+
 
 def __getattr__(name):
-    if name in ("Simulator", "native"):
-        from . import simulator, native
-        return {"Simulator": simulator.Simulator, "native": native}[name]
-    raise AttributeError(name)
+    if name == "native":
+        return importlib.import_module(".native", __name__)
+    if name == "Simulator":
+        return importlib.import_module(".simulator", __name__).Simulator
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

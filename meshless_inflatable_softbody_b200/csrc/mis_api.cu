@@ -1,0 +1,533 @@
+// mis_api.cu -- the C-ABI of include/mis.h: owns the cell-sorted structure-of-arrays
+// state of one scene and enqueues the kernels of mis_neighbors.cuh / mis_step.cuh.
+#include "../../include/mis.h"
+#include "mis_math.cuh"
+#include "mis_neighbors.cuh"
+#include "mis_sort.cuh"
+#include "mis_step.cuh"
+#include "mis_sdf.cuh"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+using namespace mis;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(MIS_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+    } while (0)
+#define CK_LAUNCH() CK(cudaGetLastError())
+
+struct MisSim {
+    int n = 0;
+    MisParams p{};
+    Consts c{};
+    int G = 8;
+    // caller-order copies
+    float* x0_orig = nullptr;
+    int* coords = nullptr;
+    int* cell_index = nullptr;
+    // sort
+    uint32_t* keys = nullptr;
+    uint32_t* perm = nullptr;
+    int* inv_perm = nullptr;
+    RadixSortTemp rs;
+    int* bounds_dev = nullptr;
+    // cell table
+    int cell_min[3] = {0, 0, 0}, cell_dim[3] = {0, 0, 0};
+    int ncells = 0, ncells_cap = 0;
+    int* cell_start = nullptr;
+    int* cell_end = nullptr;
+    int* cell_lin_sorted = nullptr;
+    // lists
+    uint32_t* nbr_count = nullptr;
+    unsigned long long* nbr_start = nullptr;
+    unsigned long long* scan_tmp = nullptr;
+    uint32_t* nbr = nullptr;
+    long long nbr_cap = 0, total_pairs = 0;
+    int* max_k_dev = nullptr;
+    int max_k = 0;
+    float d2_limit = 0.f;
+    // cell-sorted state
+    float4 *x0m = nullptr, *xv[2] = {nullptr, nullptr}, *vel = nullptr, *f1 = nullptr, *fel = nullptr;
+    float4 *fext = nullptr, *freem = nullptr, *matl = nullptr, *RS = nullptr, *Fd = nullptr;
+    float* Apq = nullptr;
+    float4* scratch4 = nullptr;       // eval / host staging
+    float* stage = nullptr;           // n*6 device staging for host-buffer variants
+    int cur = 0;
+    bool built = false, mass_set = false, material_set = false, started = false, dirty = true;
+    long long launches = 0;
+    // CUDA graph cache for step chunks
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_steps = 0, graph_cur = -1;
+    cudaStream_t graph_stream = nullptr;
+    // DeepSDF contact (extension)
+    SdfState sdf;
+};
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(T) + 64); }
+
+static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+
+extern "C" const char* mis_last_error(void) { return g_err.c_str(); }
+extern "C" const char* mis_version(void) { return "mis_b200 sm_100a (" __DATE__ ")"; }
+
+static float find_d2_limit(float h) {
+    // smallest float d2 with !(sqrtf(d2)/h < 2): the predicate is monotone in d2
+    auto pred = [h](float d2) { volatile float r = sqrtf(d2); volatile float q = r / h; return q < 2.f; };
+    uint32_t lo = 0, hi;
+    float hif = 16.f * h * h;
+    memcpy(&hi, &hif, 4);
+    while (hi - lo > 1) {          // pred(lo) true, pred(hi) false; positive floats order like their bits
+        uint32_t mid = lo + (hi - lo) / 2;
+        float mf; memcpy(&mf, &mid, 4);
+        if (pred(mf)) lo = mid; else hi = mid;
+    }
+    float out; memcpy(&out, &hi, 4);
+    return out;
+}
+
+static void make_consts(MisSim* s) {
+    const MisParams& p = s->p;
+    Consts& c = s->c;
+    const float pi = 3.14159265358979323846f;
+    c.h = p.h; c.inv_h = 1.f / p.h;
+    c.sigma = 1.f / (pi * p.h * p.h * p.h);
+    c.grad_c1 = c.sigma / (p.h * p.h);
+    c.grad_c2 = 0.75f * c.sigma / p.h;
+    c.dt = p.dt; c.half_dt2 = 0.5f * p.dt * p.dt; c.damping = p.damping;
+    c.k_col = p.k_col; c.col_range = p.col_range;
+    c.stiff_a = p.stiff_a; c.stiff_b = p.stiff_b;
+    c.identity_rot = p.identity_rot; c.euler = p.euler; c.no_contact = p.no_contact; c.symmetric_pair = p.symmetric_pair;
+}
+
+static View make_view(MisSim* s) {
+    View v;
+    v.n = s->n;
+    v.x0m = s->x0m; v.xcur = s->xv[s->cur]; v.xnext = s->xv[s->cur ^ 1];
+    v.vel = s->vel; v.f1 = s->f1; v.fel = s->fel; v.fext = s->fext; v.freem = s->freem; v.matl = s->matl;
+    v.RS = s->RS; v.Fd = s->Fd; v.Apq = s->p.keep_fields ? s->Apq : nullptr;
+    v.nbr_start = s->nbr_start; v.nbr = s->nbr;
+    return v;
+}
+
+static void drop_graph(MisSim* s) {
+    if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+    s->graph_steps = 0; s->graph_cur = -1;
+}
+
+// ------------------------------------------------------------------ create / destroy
+extern "C" int mis_create(int n, const float* x0_dev, const MisParams* params, void* stream, MisSim** out) {
+    if (!out || !params || !x0_dev || n <= 0) return fail(MIS_E_INVALID, "mis_create: bad argument");
+    if (!(params->h > 0.f) || !(params->dt > 0.f)) return fail(MIS_E_INVALID, "mis_create: h and dt must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    MisSim* s = new MisSim();
+    s->n = n; s->p = *params;
+    if (s->p.stiff_a == 0.f && s->p.stiff_b == 0.f) { s->p.stiff_a = 200.f; s->p.stiff_b = 199.f; }
+    if (s->p.tanh_k == 0.f) s->p.tanh_k = 3.f;
+    if (s->p.grid_x < 1) s->p.grid_x = 1;
+    if (s->p.grid_y < 1) s->p.grid_y = 1;
+    if (s->p.grid_z < 1) s->p.grid_z = 1;
+    int G = s->p.lanes_per_particle ? s->p.lanes_per_particle : 8;
+    if (G != 8 && G != 16 && G != 32) { delete s; return fail(MIS_E_INVALID, "lanes_per_particle must be 8, 16 or 32"); }
+    s->G = G;
+    make_consts(s);
+    s->d2_limit = find_d2_limit(s->p.h);
+    const size_t N = (size_t)n;
+#define ALLOC(ptr, cnt) do { cudaError_t e_ = dalloc(&(ptr), (cnt)); if (e_ != cudaSuccess) { int r_ = fail(MIS_E_CUDA, std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(e_)); mis_destroy(s); return r_; } } while (0)
+    ALLOC(s->x0_orig, 3 * N); ALLOC(s->coords, 3 * N); ALLOC(s->cell_index, N);
+    ALLOC(s->keys, N); ALLOC(s->perm, N); ALLOC(s->inv_perm, N);
+    s->rs.nblocks = nblk(n, RS_TILE);
+    ALLOC(s->rs.keys_alt, N); ALLOC(s->rs.vals_alt, N);
+    ALLOC(s->rs.hist, (size_t)RS_RADIX * s->rs.nblocks); ALLOC(s->rs.hist_scanned, (size_t)RS_RADIX * s->rs.nblocks + 1);
+    ALLOC(s->rs.tile_tmp, (size_t)nblk((long long)RS_RADIX * s->rs.nblocks, SCAN_TILE) + 1);
+    ALLOC(s->bounds_dev, 8); ALLOC(s->max_k_dev, 2);
+    ALLOC(s->cell_lin_sorted, N);
+    ALLOC(s->nbr_count, N); ALLOC(s->nbr_start, N + 1); ALLOC(s->scan_tmp, (size_t)nblk(n, SCAN_TILE) + 1);
+    ALLOC(s->x0m, N); ALLOC(s->xv[0], N); ALLOC(s->xv[1], N); ALLOC(s->vel, N); ALLOC(s->f1, N); ALLOC(s->fel, N);
+    ALLOC(s->fext, N); ALLOC(s->freem, N); ALLOC(s->matl, N); ALLOC(s->RS, 4 * N); ALLOC(s->Fd, 3 * N);
+    ALLOC(s->scratch4, 2 * N); ALLOC(s->stage, 6 * N);
+    if (s->p.keep_fields) ALLOC(s->Apq, 9 * N);
+#undef ALLOC
+    cudaMemsetAsync(s->x0m, 0, N * sizeof(float4), st);
+    cudaMemsetAsync(s->xv[0], 0, N * sizeof(float4), st);
+    cudaMemsetAsync(s->xv[1], 0, N * sizeof(float4), st);
+    cudaMemsetAsync(s->vel, 0, N * sizeof(float4), st);
+    cudaMemsetAsync(s->f1, 0, N * sizeof(float4), st);
+    cudaMemsetAsync(s->fel, 0, N * sizeof(float4), st);
+    cudaMemsetAsync(s->fext, 0, N * sizeof(float4), st);
+    cudaMemsetAsync(s->matl, 0, N * sizeof(float4), st);
+    cudaMemsetAsync(s->RS, 0, 4 * N * sizeof(float4), st);
+    cudaMemsetAsync(s->Fd, 0, 3 * N * sizeof(float4), st);
+    {   // free_points = 1 (sim.py:81)
+        std::vector<float4> ones(N, make_float4(1.f, 1.f, 1.f, 0.f));
+        cudaError_t e = cudaMemcpyAsync(s->freem, ones.data(), N * sizeof(float4), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { int r = fail(MIS_E_CUDA, std::string("init free_points: ") + cudaGetErrorString(e)); mis_destroy(s); return r; }
+    }
+    cudaError_t e = cudaMemcpyAsync(s->x0_orig, x0_dev, 3 * N * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) { int r = fail(MIS_E_CUDA, std::string("copy x0: ") + cudaGetErrorString(e)); mis_destroy(s); return r; }
+    int rc = mis_build_neighbors(s, stream);
+    if (rc != MIS_OK) { mis_destroy(s); return rc; }
+    *out = s;
+    return MIS_OK;
+}
+
+extern "C" int mis_destroy(MisSim* s) {
+    if (!s) return MIS_OK;
+    drop_graph(s);
+    sdf_free(s->sdf);
+    void* ptrs[] = {s->x0_orig, s->coords, s->cell_index, s->keys, s->perm, s->inv_perm, s->rs.keys_alt, s->rs.vals_alt,
+                    s->rs.hist, s->rs.hist_scanned, s->rs.tile_tmp, s->bounds_dev, s->max_k_dev, s->cell_start, s->cell_end,
+                    s->cell_lin_sorted, s->nbr_count, s->nbr_start, s->scan_tmp, s->nbr, s->x0m, s->xv[0], s->xv[1], s->vel,
+                    s->f1, s->fel, s->fext, s->freem, s->matl, s->RS, s->Fd, s->Apq, s->scratch4, s->stage};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    delete s;
+    return MIS_OK;
+}
+
+// ------------------------------------------------------------------ neighbour structure
+extern "C" int mis_build_neighbors(MisSim* s, void* stream) {
+    if (!s) return fail(MIS_E_INVALID, "null sim");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = s->n;
+    const float cw = 2.f * s->p.h;            // real(2.) * h, sim.py:127
+    const float inv_cw = 1.f / cw;
+    int hb[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
+    CK(cudaMemcpyAsync(s->bounds_dev, hb, sizeof hb, cudaMemcpyHostToDevice, st));
+    k_cell_coords<<<nblk(n, 256), 256, 0, st>>>(s->x0_orig, n, inv_cw, s->p.grid_x, s->p.grid_y, s->p.grid_z,
+                                                s->coords, s->cell_index, s->bounds_dev);
+    CK_LAUNCH(); s->launches++;
+    CK(cudaMemcpyAsync(hb, s->bounds_dev, sizeof hb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int maxdim = 0;
+    for (int a = 0; a < 3; a++) {
+        s->cell_min[a] = hb[a];
+        s->cell_dim[a] = hb[3 + a] - hb[a] + 1;
+        if (s->cell_dim[a] > maxdim) maxdim = s->cell_dim[a];
+    }
+    if (maxdim > 1024) return fail(MIS_E_UNSUPPORTED, "cell grid exceeds 1024 cells along an axis (30-bit Morton keys)");
+    long long nc = (long long)s->cell_dim[0] * s->cell_dim[1] * s->cell_dim[2];
+    if (nc > (1ll << 28)) return fail(MIS_E_UNSUPPORTED, "dense cell table larger than 2^28 cells");
+    s->ncells = (int)nc;
+    if (s->ncells > s->ncells_cap) {
+        if (s->cell_start) cudaFree(s->cell_start);
+        if (s->cell_end) cudaFree(s->cell_end);
+        s->cell_start = s->cell_end = nullptr;
+        CK(dalloc(&s->cell_start, (size_t)s->ncells));
+        CK(dalloc(&s->cell_end, (size_t)s->ncells));
+        s->ncells_cap = s->ncells;
+    }
+    CK(cudaMemsetAsync(s->cell_start, 0, (size_t)s->ncells * sizeof(int), st));
+    CK(cudaMemsetAsync(s->cell_end, 0, (size_t)s->ncells * sizeof(int), st));
+    const int3 cmin = make_int3(s->cell_min[0], s->cell_min[1], s->cell_min[2]);
+    const int3 cdim = make_int3(s->cell_dim[0], s->cell_dim[1], s->cell_dim[2]);
+    k_cell_keys<<<nblk(n, 256), 256, 0, st>>>(s->coords, n, cmin, s->keys);
+    CK_LAUNCH(); s->launches++;
+    int bits = 1;
+    while ((1 << bits) < maxdim) bits++;
+    s->launches += radix_sort_pairs(s->keys, s->perm, n, 3 * bits, s->rs, st);
+    CK_LAUNCH();
+    k_cell_table<<<nblk(n, 256), 256, 0, st>>>(s->keys, s->perm, s->coords, s->x0_orig, n, cmin, cdim,
+                                               s->cell_start, s->cell_end, s->cell_lin_sorted, s->inv_perm, s->x0m);
+    CK_LAUNCH(); s->launches++;
+    CK(cudaMemsetAsync(s->max_k_dev, 0, sizeof(int), st));
+    k_nbr_walk<<<nblk(n, 128), 128, 0, st>>>(s->x0m, s->cell_lin_sorted, s->cell_start, s->cell_end, cdim, n, s->d2_limit, 0,
+                                             nullptr, nullptr, s->nbr_count, s->max_k_dev);
+    CK_LAUNCH(); s->launches++;
+    s->launches += exclusive_scan<unsigned long long>(s->nbr_count, s->nbr_start, n, s->scan_tmp, st);
+    CK_LAUNCH();
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, s->nbr_start + n, sizeof total, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&s->max_k, s->max_k_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    s->total_pairs = (long long)total;
+    if (s->total_pairs > s->nbr_cap) {
+        if (s->nbr) cudaFree(s->nbr);
+        s->nbr = nullptr;
+        CK(dalloc(&s->nbr, (size_t)s->total_pairs + 32));
+        s->nbr_cap = s->total_pairs;
+    }
+    k_nbr_walk<<<nblk(n, 128), 128, 0, st>>>(s->x0m, s->cell_lin_sorted, s->cell_start, s->cell_end, cdim, n, s->d2_limit, 1,
+                                             s->nbr_start, s->nbr, s->nbr_count, s->max_k_dev);
+    CK_LAUNCH(); s->launches++;
+    s->built = true;
+    return MIS_OK;
+}
+
+extern "C" int mis_get_neighbor_info(MisSim* s, MisNeighborInfo* out) {
+    if (!s || !out) return fail(MIS_E_INVALID, "null argument");
+    out->total_pairs = s->total_pairs; out->max_neighbors = s->max_k; out->n = s->n;
+    for (int a = 0; a < 3; a++) { out->cell_min[a] = s->cell_min[a]; out->cell_dim[a] = s->cell_dim[a]; }
+    out->cell_width = 2.f * s->p.h;
+    return MIS_OK;
+}
+
+extern "C" int mis_export_cells(MisSim* s, int* cell_index_dev, int* cell_coords_dev, int* perm_dev, void* stream) {
+    if (!s) return fail(MIS_E_INVALID, "null sim");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t N = (size_t)s->n;
+    if (cell_index_dev) CK(cudaMemcpyAsync(cell_index_dev, s->cell_index, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (cell_coords_dev) CK(cudaMemcpyAsync(cell_coords_dev, s->coords, 3 * N * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (perm_dev) CK(cudaMemcpyAsync(perm_dev, s->perm, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return MIS_OK;
+}
+
+extern "C" int mis_export_cell_ranges(MisSim* s, int* start_dev, int* end_dev, void* stream) {
+    if (!s) return fail(MIS_E_INVALID, "null sim");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (start_dev) CK(cudaMemcpyAsync(start_dev, s->cell_start, (size_t)s->ncells * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (end_dev) CK(cudaMemcpyAsync(end_dev, s->cell_end, (size_t)s->ncells * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    return MIS_OK;
+}
+
+extern "C" int mis_export_neighbors(MisSim* s, long long* offsets_dev, int* nbr_dev, void* stream) {
+    if (!s || !offsets_dev) return fail(MIS_E_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = s->n;
+    uint32_t* counts = nullptr;
+    unsigned long long* tmp = nullptr;
+    CK(dalloc(&counts, (size_t)n));
+    CK(dalloc(&tmp, (size_t)nblk(n, SCAN_TILE) + 1));
+    k_export_counts<<<nblk(n, 256), 256, 0, st>>>(s->nbr_count, s->inv_perm, n, counts);
+    s->launches += 1 + exclusive_scan<unsigned long long>(counts, (unsigned long long*)offsets_dev, n, tmp, st);
+    if (nbr_dev) {
+        k_export_lists<<<nblk((long long)n * 32, 256), 256, 0, st>>>(s->nbr_start, s->nbr, s->inv_perm, s->perm, n, offsets_dev, nbr_dev);
+        s->launches++;
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(counts); cudaFree(tmp);
+    CK(e);
+    CK_LAUNCH();
+    return MIS_OK;
+}
+
+// ------------------------------------------------------------------ control functions
+template <int G> static void launch_volume(MisSim* s, cudaStream_t st) {
+    k_volume<G><<<nblk((long long)s->n * G, STEP_THREADS), STEP_THREADS, 0, st>>>(s->x0m, s->nbr_start, s->nbr, s->n, s->c,
+                                                                                  s->p.self_density, s->xv[0], s->xv[1], s->matl);
+}
+
+extern "C" int mis_set_mass(MisSim* s, const float* mass_dev, void* stream) {
+    if (!s || !mass_dev) return fail(MIS_E_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_gather_w<<<nblk(s->n, 256), 256, 0, st>>>(mass_dev, s->perm, s->n, s->x0m);
+    CK_LAUNCH();
+    if (s->G == 8) launch_volume<8>(s, st); else if (s->G == 16) launch_volume<16>(s, st); else launch_volume<32>(s, st);
+    CK_LAUNCH();
+    s->launches += 2;
+    s->mass_set = true; s->dirty = true;
+    return MIS_OK;
+}
+
+extern "C" int mis_set_material(MisSim* s, const float* youngs_dev, const float* poisson_dev, void* stream) {
+    if (!s || !youngs_dev || !poisson_dev) return fail(MIS_E_INVALID, "null argument");
+    k_material<<<nblk(s->n, 256), 256, 0, (cudaStream_t)stream>>>(youngs_dev, poisson_dev, s->perm, s->n, s->matl);
+    CK_LAUNCH(); s->launches++;
+    s->material_set = true; s->dirty = true;
+    return MIS_OK;
+}
+
+extern "C" int mis_set_design(MisSim* s, const float* x_dev, void* stream) {
+    if (!s || !x_dev) return fail(MIS_E_INVALID, "null argument");
+    k_design<<<nblk(s->n, 256), 256, 0, (cudaStream_t)stream>>>(x_dev, s->perm, s->n, s->p.tanh_k, s->matl);
+    CK_LAUNCH(); s->launches++;
+    s->dirty = true;
+    return MIS_OK;
+}
+
+extern "C" int mis_set_ext_force(MisSim* s, const float* f_dev, void* stream) {
+    if (!s || !f_dev) return fail(MIS_E_INVALID, "null argument");
+    k_gather_vec3<<<nblk(s->n, 256), 256, 0, (cudaStream_t)stream>>>(f_dev, s->perm, s->n, s->fext, 0);
+    CK_LAUNCH(); s->launches++;
+    s->dirty = true;
+    return MIS_OK;
+}
+
+extern "C" int mis_set_ext_force_host(MisSim* s, const float* f_host, void* stream) {
+    if (!s || !f_host) return fail(MIS_E_INVALID, "null argument");
+    CK(cudaMemcpyAsync(s->stage, f_host, 3 * (size_t)s->n * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return mis_set_ext_force(s, s->stage, stream);
+}
+
+extern "C" int mis_set_dirichlet(MisSim* s, const float* free_dev, void* stream) {
+    if (!s || !free_dev) return fail(MIS_E_INVALID, "null argument");
+    k_gather_vec3<<<nblk(s->n, 256), 256, 0, (cudaStream_t)stream>>>(free_dev, s->perm, s->n, s->freem, 0);
+    CK_LAUNCH(); s->launches++;
+    s->dirty = true;
+    return MIS_OK;
+}
+
+// ------------------------------------------------------------------ step machinery
+template <int G> static void launch_deform(MisSim* s, const View& v, cudaStream_t st) {
+    k_deform<G><<<nblk((long long)s->n * G, STEP_THREADS), STEP_THREADS, 0, st>>>(v, s->c);
+}
+template <int G> static void launch_force(MisSim* s, const View& v, int mode, cudaStream_t st) {
+    if (s->p.symmetric_pair)
+        k_force_sym<G><<<nblk((long long)s->n * G, STEP_THREADS), STEP_THREADS, 0, st>>>(v, s->c, mode);
+    else
+        k_force<G><<<nblk((long long)s->n * G, STEP_THREADS), STEP_THREADS, 0, st>>>(v, s->c, mode);
+}
+static void enqueue_deform(MisSim* s, const View& v, cudaStream_t st) {
+    if (s->G == 8) launch_deform<8>(s, v, st); else if (s->G == 16) launch_deform<16>(s, v, st); else launch_deform<32>(s, v, st);
+    s->launches++;
+}
+static void enqueue_force(MisSim* s, const View& v, int mode, cudaStream_t st) {
+    if (s->G == 8) launch_force<8>(s, v, mode, st); else if (s->G == 16) launch_force<16>(s, v, mode, st); else launch_force<32>(s, v, mode, st);
+    s->launches++;
+}
+
+// frame-0 style priming at the current x: elastic force, force_1 and the next position
+static int prime(MisSim* s, cudaStream_t st) {
+    if (!s->mass_set || !s->material_set) return fail(MIS_E_STATE, "set_mass and set_material must precede startup/step");
+    if (!s->p.euler) {
+        View v = make_view(s);
+        enqueue_deform(s, v, st);
+        enqueue_force(s, v, MODE_PRIME, st);
+        CK_LAUNCH();
+    }
+    s->dirty = false;
+    return MIS_OK;
+}
+
+extern "C" int mis_startup(MisSim* s, const float v0[3], void* stream) {
+    if (!s || !v0) return fail(MIS_E_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    s->cur = 0;
+    k_startup<<<nblk(s->n, 256), 256, 0, st>>>(s->x0m, s->n, make_float3(v0[0], v0[1], v0[2]), s->xv[0], s->vel);
+    CK_LAUNCH(); s->launches++;
+    s->started = true; s->dirty = true;
+    return MIS_OK;
+}
+
+extern "C" int mis_set_state(MisSim* s, const float* x_dev, const float* v_dev, void* stream) {
+    if (!s || !x_dev || !v_dev) return fail(MIS_E_INVALID, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    k_gather_vec3<<<nblk(s->n, 256), 256, 0, st>>>(x_dev, s->perm, s->n, s->xv[s->cur], 1);
+    k_gather_vec3<<<nblk(s->n, 256), 256, 0, st>>>(v_dev, s->perm, s->n, s->vel, 0);
+    CK_LAUNCH(); s->launches += 2;
+    s->started = true; s->dirty = true;
+    return MIS_OK;
+}
+
+static void enqueue_one_step(MisSim* s, cudaStream_t st) {
+    if (s->p.euler) {
+        // sim_taichi.py:174-182: forces at frame f, then advance to f+1
+        View v = make_view(s);
+        enqueue_deform(s, v, st);
+        enqueue_force(s, v, MODE_EULER, st);
+        s->cur ^= 1;
+    } else {
+        s->cur ^= 1;                       // part_1 of this step was fused into the previous force kernel
+        View v = make_view(s);
+        enqueue_deform(s, v, st);
+        enqueue_force(s, v, MODE_STEP, st);
+    }
+}
+
+extern "C" int mis_step(MisSim* s, int n_steps, void* stream) {
+    if (!s || n_steps < 0) return fail(MIS_E_INVALID, "bad argument");
+    if (!s->started) return fail(MIS_E_STATE, "mis_step before mis_startup / mis_set_state");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->dirty) { int rc = prime(s, st); if (rc) return rc; }
+    int chunk = s->p.graph_steps > 0 ? s->p.graph_steps : 32;
+    chunk &= ~1;                           // even: the ping-pong index returns to its start
+    int done = 0;
+    const bool can_graph = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+    if (chunk >= 2 && s->p.graph_steps >= 0 && can_graph) {
+        while (n_steps - done >= chunk) {
+            if (!s->graph_exec || s->graph_steps != chunk || s->graph_cur != s->cur || s->graph_stream != st) {
+                drop_graph(s);
+                cudaGraph_t g = nullptr;
+                long long l0 = s->launches;
+                CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                int cur0 = s->cur;
+                for (int k = 0; k < chunk; k++) enqueue_one_step(s, st);
+                cudaError_t e = cudaStreamEndCapture(st, &g);
+                s->cur = cur0;
+                s->launches = l0;
+                if (e != cudaSuccess) return fail(MIS_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+                e = cudaGraphInstantiate(&s->graph_exec, g, 0);
+                cudaGraphDestroy(g);
+                if (e != cudaSuccess) { s->graph_exec = nullptr; return fail(MIS_E_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e)); }
+                s->graph_steps = chunk; s->graph_cur = s->cur; s->graph_stream = st;
+            }
+            CK(cudaGraphLaunch(s->graph_exec, st));
+            s->launches += 2ll * chunk;
+            done += chunk;                 // cur unchanged after an even number of steps
+        }
+    }
+    for (; done < n_steps; done++) enqueue_one_step(s, st);
+    CK_LAUNCH();
+    return MIS_OK;
+}
+
+extern "C" int mis_get_state(MisSim* s, float* x_dev, float* v_dev, void* stream) {
+    if (!s) return fail(MIS_E_INVALID, "null sim");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (x_dev) { k_export_vec3<<<nblk(s->n, 256), 256, 0, st>>>(s->xv[s->cur], s->inv_perm, s->n, x_dev); s->launches++; }
+    if (v_dev) { k_export_vec3<<<nblk(s->n, 256), 256, 0, st>>>(s->vel, s->inv_perm, s->n, v_dev); s->launches++; }
+    CK_LAUNCH();
+    return MIS_OK;
+}
+
+extern "C" int mis_get_state_host(MisSim* s, float* x_host, float* v_host, void* stream) {
+    if (!s) return fail(MIS_E_INVALID, "null sim");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t N3 = 3 * (size_t)s->n;
+    int rc = mis_get_state(s, x_host ? s->stage : nullptr, v_host ? s->stage + N3 : nullptr, stream);
+    if (rc) return rc;
+    if (x_host) CK(cudaMemcpyAsync(x_host, s->stage, N3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (v_host) CK(cudaMemcpyAsync(v_host, s->stage + N3, N3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return MIS_OK;
+}
+
+extern "C" int mis_get_fields(MisSim* s, float* A_dev, float* R_dev, float* F_dev, float* S_dev,
+                              float* fel_dev, float* rho_dev, float* vol_dev, void* stream) {
+    if (!s) return fail(MIS_E_INVALID, "null sim");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->started && s->dirty) { int rc = prime(s, st); if (rc) return rc; }
+    View v = make_view(s);
+    v.Apq = s->Apq;
+    if (A_dev && !s->Apq) return fail(MIS_E_STATE, "A_pq export needs MisParams.keep_fields = 1");
+    const int g = nblk(s->n, 256);
+    if (R_dev) { k_export_field<<<g, 256, 0, st>>>(v, s->inv_perm, 0, R_dev); s->launches++; }
+    if (S_dev) { k_export_field<<<g, 256, 0, st>>>(v, s->inv_perm, 1, S_dev); s->launches++; }
+    if (F_dev) { k_export_field<<<g, 256, 0, st>>>(v, s->inv_perm, 2, F_dev); s->launches++; }
+    if (A_dev) { k_export_field<<<g, 256, 0, st>>>(v, s->inv_perm, 3, A_dev); s->launches++; }
+    if (rho_dev) { k_export_field<<<g, 256, 0, st>>>(v, s->inv_perm, 4, rho_dev); s->launches++; }
+    if (vol_dev) { k_export_field<<<g, 256, 0, st>>>(v, s->inv_perm, 5, vol_dev); s->launches++; }
+    if (fel_dev) { k_export_vec3<<<g, 256, 0, st>>>(s->fel, s->inv_perm, s->n, fel_dev); s->launches++; }
+    CK_LAUNCH();
+    return MIS_OK;
+}
+
+extern "C" int mis_eval_forces(MisSim* s, const float* x_dev, float* fel_dev, void* stream) {
+    if (!s || !x_dev || !fel_dev) return fail(MIS_E_INVALID, "null argument");
+    if (!s->mass_set || !s->material_set) return fail(MIS_E_STATE, "set_mass and set_material must precede mis_eval_forces");
+    cudaStream_t st = (cudaStream_t)stream;
+    // scratch position buffer carrying the volumes in .w
+    CK(cudaMemcpyAsync(s->scratch4, s->xv[s->cur], (size_t)s->n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    k_gather_vec3<<<nblk(s->n, 256), 256, 0, st>>>(x_dev, s->perm, s->n, s->scratch4, 1);
+    s->launches++;
+    View v = make_view(s);
+    v.xcur = s->scratch4; v.xnext = s->scratch4 + s->n; v.fel = s->scratch4 + s->n;
+    enqueue_deform(s, v, st);
+    enqueue_force(s, v, MODE_EVAL, st);
+    k_export_vec3<<<nblk(s->n, 256), 256, 0, st>>>(s->scratch4 + s->n, s->inv_perm, s->n, fel_dev);
+    s->launches++;
+    CK_LAUNCH();
+    s->dirty = true;                      // R, S, F now describe x_dev, not the current frame
+    return MIS_OK;
+}
+
+extern "C" long long mis_launch_count(MisSim* s) { return s ? s->launches : 0; }

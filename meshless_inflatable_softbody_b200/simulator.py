@@ -1,0 +1,252 @@
+"""Simulator: the reference's script-level control functions on one object.
+
+The reference has no class; its public surface is module-level functions and arrays
+(sim.py:279-308 setters, :261-266 startup, :341-372 diff_sim, position[f].numpy()).  The
+method names and argument meaning below are those; the arithmetic runs in the CUDA library
+behind include/mis.h.  There is no CPU path here: without a CUDA device and the built
+library, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import native
+from .config import SceneConfig
+
+
+def hash_grid_dims(x0: np.ndarray, h: float):
+    """sim.py:123-125: int(2 * (max - min) / float(h) / 3) per axis (float(h) = the fp32 value)."""
+    hf = float(np.float32(h))
+    p = np.asarray(x0, dtype=np.float64)
+    return tuple(max(1, int(2 * (p[:, a].max() - p[:, a].min()) / hf / 3)) for a in range(3))
+
+
+class Simulator:
+    def __init__(self, x0, config: Optional[SceneConfig] = None, device: str = "cuda:0",
+                 lanes_per_particle: int = 0, keep_fields: bool = False, graph_steps: int = 0,
+                 apply_defaults: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("meshless_inflatable_softbody_b200.Simulator needs a CUDA device (sm_100a); "
+                               "there is no CPU fallback")
+        self.cfg = config or SceneConfig()
+        self.device = torch.device(device)
+        self.L = native.lib()
+        x0_np = np.ascontiguousarray(np.asarray(x0, dtype=np.float32).reshape(-1, 3))
+        self.n = int(x0_np.shape[0])
+        self.x0 = torch.from_numpy(x0_np).to(self.device)
+        gx, gy, gz = hash_grid_dims(x0_np, self.cfg.h)
+        c = self.cfg
+        p = native.MisParams()
+        p.h, p.damping, p.dt = c.h, c.damping, c.time_step
+        p.k_col, p.col_range = c.collision_penalty_stiffness, c.collision_range
+        p.stiff_a, p.stiff_b, p.tanh_k = c.stiffness_a, c.stiffness_b, c.tanh_k
+        p.grid_x, p.grid_y, p.grid_z = gx, gy, gz
+        p.symmetric_pair, p.identity_rot = int(c.symmetric_pair), int(c.identity_rotation)
+        p.self_density, p.euler, p.no_contact = int(c.self_density), int(c.euler), int(not c.ground_contact)
+        p.lanes_per_particle, p.keep_fields, p.graph_steps = int(lanes_per_particle), int(keep_fields), int(graph_steps)
+        self.params = p
+        self.hash_grid = (gx, gy, gz)
+        with torch.cuda.device(self.device):
+            self.stream = torch.cuda.Stream(device=self.device)
+        self._h = C.c_void_p()
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        native.check(self.L.mis_create(self.n, self.x0.data_ptr(), C.byref(p), self._st(), C.byref(self._h)), "mis_create")
+        self.frame = 0
+        if apply_defaults:      # main(), sim.py:441-444 + x.fill_(-1.), sim.py:99
+            self.set_all_external_force(c.external_force)
+            self.set_youngs_modulus(c.youngs_modulus)
+            self.set_poisson_ratio(c.poisson_ratio)
+            self.set_mass(c.mass)
+            self.set_design(c.design_x)
+
+    # ------------------------------------------------------------------ plumbing
+    def _st(self):
+        return C.c_void_p(self.stream.cuda_stream)
+
+    def _dev(self, a, shape):
+        """Broadcast a scalar / sequence / array / tensor to a contiguous fp32 device tensor."""
+        if isinstance(a, torch.Tensor):
+            t = a.to(device=self.device, dtype=torch.float32)
+        else:
+            t = torch.as_tensor(np.asarray(a, dtype=np.float32), device=self.device)
+        t = t.expand(shape).contiguous()
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        return t
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.synchronize()
+            self.L.mis_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self.stream.synchronize()
+
+    # ------------------------------------------------------------------ control functions (sim.py:279-308)
+    def set_all_external_force(self, f: Sequence[float]):
+        self._fext = self._dev(f, (self.n, 3)).clone()
+        native.check(self.L.mis_set_ext_force(self._h, self._fext.data_ptr(), self._st()), "mis_set_ext_force")
+
+    def set_external_force(self, i, f):
+        """sim.py:279-280; i may be an index or an index array."""
+        self._fext[i] = torch.as_tensor(np.asarray(f, np.float32), device=self.device)
+        native.check(self.L.mis_set_ext_force(self._h, self._fext.data_ptr(), self._st()), "mis_set_ext_force")
+
+    def set_external_forces(self, f):
+        self._fext = self._dev(f, (self.n, 3)).clone()
+        native.check(self.L.mis_set_ext_force(self._h, self._fext.data_ptr(), self._st()), "mis_set_ext_force")
+
+    def set_external_forces_host(self, f_host: torch.Tensor):
+        """Per-step input path: (n,3) fp32 pinned host tensor, copied inside the library."""
+        native.check(self.L.mis_set_ext_force_host(self._h, f_host.data_ptr(), self._st()), "mis_set_ext_force_host")
+
+    def set_dirichlet(self, i, d):
+        """sim.py:285-286: free_points[i] = d (component-wise multiplier)."""
+        if not hasattr(self, "_free"):
+            self._free = torch.ones((self.n, 3), device=self.device, dtype=torch.float32)
+        self._free[i] = torch.as_tensor(np.asarray(d, np.float32), device=self.device)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        native.check(self.L.mis_set_dirichlet(self._h, self._free.data_ptr(), self._st()), "mis_set_dirichlet")
+
+    def set_youngs_modulus(self, E):
+        self._E = self._dev(E, (self.n,)).clone()
+        if hasattr(self, "_nu"):
+            native.check(self.L.mis_set_material(self._h, self._E.data_ptr(), self._nu.data_ptr(), self._st()), "mis_set_material")
+
+    def set_poisson_ratio(self, nu):
+        self._nu = self._dev(nu, (self.n,)).clone()
+        if hasattr(self, "_E"):
+            native.check(self.L.mis_set_material(self._h, self._E.data_ptr(), self._nu.data_ptr(), self._st()), "mis_set_material")
+
+    def set_mass(self, m):
+        self._m = self._dev(m, (self.n,)).clone()
+        native.check(self.L.mis_set_mass(self._h, self._m.data_ptr(), self._st()), "mis_set_mass")
+
+    def set_design(self, x):
+        """x -> ratio = 0.5 tanh(k x) + 0.5 (compute_ratio, sim.py:107-110)."""
+        self._x = self._dev(x, (self.n,)).clone()
+        native.check(self.L.mis_set_design(self._h, self._x.data_ptr(), self._st()), "mis_set_design")
+
+    # ------------------------------------------------------------------ rollout (sim.py:341-358)
+    def startup(self, v0: Optional[Sequence[float]] = None):
+        v = (C.c_float * 3)(*(v0 if v0 is not None else self.cfg.initial_velocity))
+        native.check(self.L.mis_startup(self._h, v, self._st()), "mis_startup")
+        self.frame = 0
+
+    def set_state(self, x, v, frame: int = 0):
+        xd, vd = self._dev(x, (self.n, 3)), self._dev(v, (self.n, 3))
+        native.check(self.L.mis_set_state(self._h, xd.data_ptr(), vd.data_ptr(), self._st()), "mis_set_state")
+        self.stream.synchronize()
+        self.frame = frame
+
+    def step(self, n_steps: int = 1):
+        native.check(self.L.mis_step(self._h, int(n_steps), self._st()), "mis_step")
+        self.frame += int(n_steps)
+
+    def rebuild_neighbors(self):
+        native.check(self.L.mis_build_neighbors(self._h, self._st()), "mis_build_neighbors")
+
+    # ------------------------------------------------------------------ state export
+    def position_velocity(self):
+        x = torch.empty((self.n, 3), device=self.device, dtype=torch.float32)
+        v = torch.empty((self.n, 3), device=self.device, dtype=torch.float32)
+        native.check(self.L.mis_get_state(self._h, x.data_ptr(), v.data_ptr(), self._st()), "mis_get_state")
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        return x, v
+
+    def position(self) -> torch.Tensor:
+        """position[f] in the caller's particle order (sim.py:334)."""
+        return self.position_velocity()[0]
+
+    def velocity(self) -> torch.Tensor:
+        return self.position_velocity()[1]
+
+    def get_state_host(self, x_host: torch.Tensor, v_host: Optional[torch.Tensor] = None):
+        native.check(self.L.mis_get_state_host(self._h, x_host.data_ptr(), v_host.data_ptr() if v_host is not None else None,
+                                               self._st()), "mis_get_state_host")
+
+    def fields(self, want=("R", "F", "S", "fel", "rho", "vol")):
+        out = {}
+        shapes = {"A": (self.n, 3, 3), "R": (self.n, 3, 3), "F": (self.n, 3, 3), "S": (self.n, 3, 3),
+                  "fel": (self.n, 3), "rho": (self.n,), "vol": (self.n,)}
+        ptr = {}
+        for k in ("A", "R", "F", "S", "fel", "rho", "vol"):
+            if k in want:
+                out[k] = torch.empty(shapes[k], device=self.device, dtype=torch.float32)
+                ptr[k] = out[k].data_ptr()
+            else:
+                ptr[k] = None
+        native.check(self.L.mis_get_fields(self._h, ptr["A"], ptr["R"], ptr["F"], ptr["S"], ptr["fel"], ptr["rho"], ptr["vol"],
+                                           self._st()), "mis_get_fields")
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        return out
+
+    def eval_forces(self, x) -> torch.Tensor:
+        xd = self._dev(x, (self.n, 3))
+        f = torch.empty((self.n, 3), device=self.device, dtype=torch.float32)
+        native.check(self.L.mis_eval_forces(self._h, xd.data_ptr(), f.data_ptr(), self._st()), "mis_eval_forces")
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        self.stream.synchronize()
+        return f
+
+    def export_targets(self, folder: str, every: Optional[int] = None, count: Optional[int] = None):
+        """sim.py:363-369: position_{i}.npy / velocity_{i}.npy for i = 1..count at frames every*i.
+
+        Runs the rollout from the current frame; the files are (n,3) fp32 in caller order.
+        """
+        count = count or self.cfg.target_frames
+        every = every or (self.cfg.frames // self.cfg.target_frames)
+        os.makedirs(folder, exist_ok=True)
+        for i in range(1, count + 1):
+            target = every * i
+            if target > self.frame:
+                self.step(target - self.frame)
+            x, v = self.position_velocity()
+            np.save(os.path.join(folder, f"position_{i}.npy"), x.cpu().numpy())
+            np.save(os.path.join(folder, f"velocity_{i}.npy"), v.cpu().numpy())
+
+    # ------------------------------------------------------------------ neighbour structure (bit-exact checks)
+    def neighbor_info(self) -> native.MisNeighborInfo:
+        info = native.MisNeighborInfo()
+        native.check(self.L.mis_get_neighbor_info(self._h, C.byref(info)), "mis_get_neighbor_info")
+        return info
+
+    def cells(self):
+        ci = torch.empty(self.n, device=self.device, dtype=torch.int32)
+        cc = torch.empty((self.n, 3), device=self.device, dtype=torch.int32)
+        pm = torch.empty(self.n, device=self.device, dtype=torch.int32)
+        native.check(self.L.mis_export_cells(self._h, ci.data_ptr(), cc.data_ptr(), pm.data_ptr(), self._st()), "mis_export_cells")
+        self.stream.synchronize()
+        return ci, cc, pm
+
+    def cell_ranges(self):
+        info = self.neighbor_info()
+        nc = info.cell_dim[0] * info.cell_dim[1] * info.cell_dim[2]
+        s = torch.empty(nc, device=self.device, dtype=torch.int32)
+        e = torch.empty(nc, device=self.device, dtype=torch.int32)
+        native.check(self.L.mis_export_cell_ranges(self._h, s.data_ptr(), e.data_ptr(), self._st()), "mis_export_cell_ranges")
+        self.stream.synchronize()
+        return s, e
+
+    def neighbors(self):
+        info = self.neighbor_info()
+        off = torch.empty(self.n + 1, device=self.device, dtype=torch.int64)
+        nb = torch.empty(max(1, info.total_pairs), device=self.device, dtype=torch.int32)
+        native.check(self.L.mis_export_neighbors(self._h, off.data_ptr(), nb.data_ptr(), self._st()), "mis_export_neighbors")
+        self.stream.synchronize()
+        return off, nb[: info.total_pairs]
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.L.mis_launch_count(self._h))

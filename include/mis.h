@@ -132,8 +132,11 @@ int mis_get_fields(MisSim* sim, float* A_dev, float* R_dev, float* F_dev, float*
 int mis_eval_forces(MisSim* sim, const float* x_dev, float* fel_dev, void* stream);
 /* number of kernels this sim has launched so far (bench.py's gpu_launches)           */
 long long mis_launch_count(MisSim* sim);
-/* device time of the most recent mis_step split per kernel family is taken by the
- * caller with CUDA events; these return the kernel names for reports.               */
+/* Measurement aid: n_steps steps with a CUDA event pair around every kernel launch on
+ * `stream`; returns the summed device milliseconds of the deform (compute_A_pq +
+ * compute_nabla_u) and force (compute_elastic_forces + part_2/part_1) kernels.
+ * Advances the state like mis_step.  Synchronises the host.                          */
+int mis_profile_step(MisSim* sim, int n_steps, void* stream, double* ms_deform, double* ms_force);
 
 #ifdef __cplusplus
 }

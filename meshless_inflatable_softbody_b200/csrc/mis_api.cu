@@ -531,3 +531,37 @@ extern "C" int mis_eval_forces(MisSim* s, const float* x_dev, float* fel_dev, vo
 }
 
 extern "C" long long mis_launch_count(MisSim* s) { return s ? s->launches : 0; }
+
+// n_steps steps launched one kernel at a time with a CUDA event pair around each launch on
+// `stream`; returns the summed device time per kernel family.  Synchronises the host.
+extern "C" int mis_profile_step(MisSim* s, int n_steps, void* stream, double* ms_deform, double* ms_force) {
+    if (!s || n_steps <= 0) return fail(MIS_E_INVALID, "bad argument");
+    if (!s->started) return fail(MIS_E_STATE, "mis_profile_step before mis_startup / mis_set_state");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->dirty) { int rc = prime(s, st); if (rc) return rc; }
+    std::vector<cudaEvent_t> ev(3 * (size_t)n_steps);
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    for (int k = 0; k < n_steps; k++) {
+        if (!s->p.euler) s->cur ^= 1;
+        View v = make_view(s);
+        CK(cudaEventRecord(ev[3 * k + 0], st));
+        enqueue_deform(s, v, st);
+        CK(cudaEventRecord(ev[3 * k + 1], st));
+        enqueue_force(s, v, s->p.euler ? MODE_EULER : MODE_STEP, st);
+        CK(cudaEventRecord(ev[3 * k + 2], st));
+        if (s->p.euler) s->cur ^= 1;
+    }
+    CK(cudaStreamSynchronize(st));
+    double a = 0, b = 0;
+    for (int k = 0; k < n_steps; k++) {
+        float t0 = 0, t1 = 0;
+        cudaEventElapsedTime(&t0, ev[3 * k + 0], ev[3 * k + 1]);
+        cudaEventElapsedTime(&t1, ev[3 * k + 1], ev[3 * k + 2]);
+        a += t0; b += t1;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (ms_deform) *ms_deform = a;
+    if (ms_force) *ms_force = b;
+    CK_LAUNCH();
+    return MIS_OK;
+}

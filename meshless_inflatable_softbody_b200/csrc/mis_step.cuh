@@ -282,6 +282,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_force(View s, Consts c, int mo
         fel.x = hv * (ax + r0.x * ux + r0.y * uy + r0.z * uz);
         fel.y = hv * (ay + r0.w * ux + r1.x * uy + r1.y * uz);
         fel.z = hv * (az + r1.z * ux + r1.w * uy + r2.x * uz);
+        if (b == e) fel = make_float3(0.f, 0.f, 0.f);   // isolated particle: the reference loop never runs (V = m/0)
         integrate_epilogue(s, c, i, fel, mode, p0i, s.xcur[i]);
     }
 }
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_force_sym(View s, Consts c, in
         fel.x = hv * (ax + r0.x * ux + r0.y * uy + r0.z * uz);
         fel.y = hv * (ay + r0.w * ux + r1.x * uy + r1.y * uz);
         fel.z = hv * (az + r1.z * ux + r1.w * uy + r2.x * uz);
+        if (b == e) fel = make_float3(0.f, 0.f, 0.f);   // isolated particle: the reference loop never runs (V = m/0)
         integrate_epilogue(s, c, i, fel, mode, p0i, s.xcur[i]);
     }
 }

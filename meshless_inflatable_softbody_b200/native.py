@@ -96,6 +96,7 @@ SYMBOLS = {
     "mis_get_fields": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp]),
     "mis_eval_forces": (C.c_int, [_vp, _fp, _fp, _vp]),
     "mis_launch_count": (C.c_longlong, [_vp]),
+    "mis_profile_step": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -247,6 +247,13 @@ class Simulator:
         self.stream.synchronize()
         return off, nb[: info.total_pairs]
 
+    def profile_step(self, n_steps: int):
+        """Device milliseconds summed over n_steps for (deform kernel, force kernel); advances the state."""
+        a, b = C.c_double(0), C.c_double(0)
+        native.check(self.L.mis_profile_step(self._h, int(n_steps), self._st(), C.byref(a), C.byref(b)), "mis_profile_step")
+        self.frame += int(n_steps)
+        return a.value, b.value
+
     @property
     def launch_count(self) -> int:
         return int(self.L.mis_launch_count(self._h))

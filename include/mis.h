@@ -57,7 +57,8 @@ typedef struct MisParams {
     /* tuning (0 = library default) */
     int   lanes_per_particle;/* 8, 16 or 32 lanes cooperate on one particle         */
     int   keep_fields;       /* 1: also store A_pq each step (diagnostics export)   */
-    int   graph_steps;       /* steps per captured CUDA graph chunk (0 = default)   */
+    int   graph_steps;       /* steps per captured CUDA graph chunk (0 = default 32, <0 = no graphs) */
+    int   two_pass_deform;   /* 1: def_grad with the reference's two-loop order (sim.py:203-208)  */
 } MisParams;
 
 typedef struct MisNeighborInfo {
@@ -89,8 +90,9 @@ int mis_get_neighbor_info(MisSim* sim, MisNeighborInfo* out);
 /* Bit-exact checks against the reference structures.  Any pointer may be NULL.
  *   cell_index_dev[n]   : wp.HashGrid linear cell index of each particle (caller order)
  *   cell_coords_dev[3n] : integer cell coordinates int(p / cell_width) (caller order)
- *   perm_dev[n]         : caller id of the particle in sorted slot s (cell-sorted order,
- *                         ascending caller id inside a cell = hash_grid_point_id)     */
+ *   perm_dev[n]         : caller id of the particle in sorted slot s.  Cells are contiguous slot
+ *                         ranges; inside a cell particles follow a fine Morton curve, then caller id.
+ *                         (hash_grid_point_id's order is the stable argsort of cell_index.)   */
 int mis_export_cells(MisSim* sim, int* cell_index_dev, int* cell_coords_dev, int* perm_dev, void* stream);
 /* dense cell table over cell_dim (x fastest): sorted-slot range [start, end) per cell */
 int mis_export_cell_ranges(MisSim* sim, int* start_dev, int* end_dev, void* stream);

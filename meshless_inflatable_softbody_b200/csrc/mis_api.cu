@@ -37,6 +37,8 @@ struct MisSim {
     int* cell_index = nullptr;
     // sort
     uint32_t* keys = nullptr;
+    uint32_t* subkey = nullptr;
+    int sub_bits = 0;
     uint32_t* perm = nullptr;
     int* inv_perm = nullptr;
     RadixSortTemp rs;
@@ -58,7 +60,7 @@ struct MisSim {
     float d2_limit = 0.f;
     // cell-sorted state
     float4 *x0m = nullptr, *xv[2] = {nullptr, nullptr}, *vel = nullptr, *f1 = nullptr, *fel = nullptr;
-    float4 *fext = nullptr, *freem = nullptr, *matl = nullptr, *RS = nullptr, *Fd = nullptr;
+    float4 *fext = nullptr, *freem = nullptr, *matl = nullptr, *RS = nullptr, *Fd = nullptr, *Ks = nullptr;
     float* Apq = nullptr;
     float4* scratch4 = nullptr;       // eval / host staging
     float* stage = nullptr;           // n*6 device staging for host-buffer variants
@@ -115,7 +117,7 @@ static View make_view(MisSim* s) {
     v.n = s->n;
     v.x0m = s->x0m; v.xcur = s->xv[s->cur]; v.xnext = s->xv[s->cur ^ 1];
     v.vel = s->vel; v.f1 = s->f1; v.fel = s->fel; v.fext = s->fext; v.freem = s->freem; v.matl = s->matl;
-    v.RS = s->RS; v.Fd = s->Fd; v.Apq = s->p.keep_fields ? s->Apq : nullptr;
+    v.RS = s->RS; v.Fd = s->Fd; v.Ks = s->Ks; v.Apq = s->p.keep_fields ? s->Apq : nullptr;
     v.nbr_start = s->nbr_start; v.nbr = s->nbr;
     return v;
 }
@@ -145,7 +147,7 @@ extern "C" int mis_create(int n, const float* x0_dev, const MisParams* params, v
     const size_t N = (size_t)n;
 #define ALLOC(ptr, cnt) do { cudaError_t e_ = dalloc(&(ptr), (cnt)); if (e_ != cudaSuccess) { int r_ = fail(MIS_E_CUDA, std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(e_)); mis_destroy(s); return r_; } } while (0)
     ALLOC(s->x0_orig, 3 * N); ALLOC(s->coords, 3 * N); ALLOC(s->cell_index, N);
-    ALLOC(s->keys, N); ALLOC(s->perm, N); ALLOC(s->inv_perm, N);
+    ALLOC(s->keys, N); ALLOC(s->subkey, N); ALLOC(s->perm, N); ALLOC(s->inv_perm, N);
     s->rs.nblocks = nblk(n, RS_TILE);
     ALLOC(s->rs.keys_alt, N); ALLOC(s->rs.vals_alt, N);
     ALLOC(s->rs.hist, (size_t)RS_RADIX * s->rs.nblocks); ALLOC(s->rs.hist_scanned, (size_t)RS_RADIX * s->rs.nblocks + 1);
@@ -154,7 +156,7 @@ extern "C" int mis_create(int n, const float* x0_dev, const MisParams* params, v
     ALLOC(s->cell_lin_sorted, N);
     ALLOC(s->nbr_count, N); ALLOC(s->nbr_start, N + 1); ALLOC(s->scan_tmp, (size_t)nblk(n, SCAN_TILE) + 1);
     ALLOC(s->x0m, N); ALLOC(s->xv[0], N); ALLOC(s->xv[1], N); ALLOC(s->vel, N); ALLOC(s->f1, N); ALLOC(s->fel, N);
-    ALLOC(s->fext, N); ALLOC(s->freem, N); ALLOC(s->matl, N); ALLOC(s->RS, 4 * N); ALLOC(s->Fd, 3 * N);
+    ALLOC(s->fext, N); ALLOC(s->freem, N); ALLOC(s->matl, N); ALLOC(s->RS, 4 * N); ALLOC(s->Fd, 3 * N); ALLOC(s->Ks, 3 * N);
     ALLOC(s->scratch4, 2 * N); ALLOC(s->stage, 6 * N);
     if (s->p.keep_fields) ALLOC(s->Apq, 9 * N);
 #undef ALLOC
@@ -168,6 +170,7 @@ extern "C" int mis_create(int n, const float* x0_dev, const MisParams* params, v
     cudaMemsetAsync(s->matl, 0, N * sizeof(float4), st);
     cudaMemsetAsync(s->RS, 0, 4 * N * sizeof(float4), st);
     cudaMemsetAsync(s->Fd, 0, 3 * N * sizeof(float4), st);
+    cudaMemsetAsync(s->Ks, 0, 3 * N * sizeof(float4), st);
     {   // free_points = 1 (sim.py:81)
         std::vector<float4> ones(N, make_float4(1.f, 1.f, 1.f, 0.f));
         cudaError_t e = cudaMemcpyAsync(s->freem, ones.data(), N * sizeof(float4), cudaMemcpyHostToDevice, st);
@@ -186,7 +189,7 @@ extern "C" int mis_destroy(MisSim* s) {
     if (!s) return MIS_OK;
     drop_graph(s);
     sdf_free(s->sdf);
-    void* ptrs[] = {s->x0_orig, s->coords, s->cell_index, s->keys, s->perm, s->inv_perm, s->rs.keys_alt, s->rs.vals_alt,
+    void* ptrs[] = {s->x0_orig, s->coords, s->cell_index, s->keys, s->subkey, s->Ks, s->perm, s->inv_perm, s->rs.keys_alt, s->rs.vals_alt,
                     s->rs.hist, s->rs.hist_scanned, s->rs.tile_tmp, s->bounds_dev, s->max_k_dev, s->cell_start, s->cell_end,
                     s->cell_lin_sorted, s->nbr_count, s->nbr_start, s->scan_tmp, s->nbr, s->x0m, s->xv[0], s->xv[1], s->vel,
                     s->f1, s->fel, s->fext, s->freem, s->matl, s->RS, s->Fd, s->Apq, s->scratch4, s->stage};
@@ -205,7 +208,7 @@ extern "C" int mis_build_neighbors(MisSim* s, void* stream) {
     int hb[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
     CK(cudaMemcpyAsync(s->bounds_dev, hb, sizeof hb, cudaMemcpyHostToDevice, st));
     k_cell_coords<<<nblk(n, 256), 256, 0, st>>>(s->x0_orig, n, inv_cw, s->p.grid_x, s->p.grid_y, s->p.grid_z,
-                                                s->coords, s->cell_index, s->bounds_dev);
+                                                s->coords, s->cell_index, s->subkey, s->bounds_dev);
     CK_LAUNCH(); s->launches++;
     CK(cudaMemcpyAsync(hb, s->bounds_dev, sizeof hb, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -231,13 +234,15 @@ extern "C" int mis_build_neighbors(MisSim* s, void* stream) {
     CK(cudaMemsetAsync(s->cell_end, 0, (size_t)s->ncells * sizeof(int), st));
     const int3 cmin = make_int3(s->cell_min[0], s->cell_min[1], s->cell_min[2]);
     const int3 cdim = make_int3(s->cell_dim[0], s->cell_dim[1], s->cell_dim[2]);
-    k_cell_keys<<<nblk(n, 256), 256, 0, st>>>(s->coords, n, cmin, s->keys);
-    CK_LAUNCH(); s->launches++;
     int bits = 1;
     while ((1 << bits) < maxdim) bits++;
-    s->launches += radix_sort_pairs(s->keys, s->perm, n, 3 * bits, s->rs, st);
+    // in-cell Morton refinement: as many of its 9 bits as fit a 32-bit key (multiples of 3)
+    s->sub_bits = 3 * bits + 9 <= 32 ? 9 : (3 * bits + 6 <= 32 ? 6 : (3 * bits + 3 <= 32 ? 3 : 0));
+    k_cell_keys<<<nblk(n, 256), 256, 0, st>>>(s->coords, s->subkey, n, cmin, s->sub_bits, s->keys);
+    CK_LAUNCH(); s->launches++;
+    s->launches += radix_sort_pairs(s->keys, s->perm, n, 3 * bits + s->sub_bits, s->rs, st);
     CK_LAUNCH();
-    k_cell_table<<<nblk(n, 256), 256, 0, st>>>(s->keys, s->perm, s->coords, s->x0_orig, n, cmin, cdim,
+    k_cell_table<<<nblk(n, 256), 256, 0, st>>>(s->keys, s->perm, s->coords, s->x0_orig, n, cmin, cdim, s->sub_bits,
                                                s->cell_start, s->cell_end, s->cell_lin_sorted, s->inv_perm, s->x0m);
     CK_LAUNCH(); s->launches++;
     CK(cudaMemsetAsync(s->max_k_dev, 0, sizeof(int), st));
@@ -315,6 +320,7 @@ extern "C" int mis_export_neighbors(MisSim* s, long long* offsets_dev, int* nbr_
 template <int G> static void launch_volume(MisSim* s, cudaStream_t st) {
     k_volume<G><<<nblk((long long)s->n * G, STEP_THREADS), STEP_THREADS, 0, st>>>(s->x0m, s->nbr_start, s->nbr, s->n, s->c,
                                                                                   s->p.self_density, s->xv[0], s->xv[1], s->matl);
+    k_static_K<G><<<nblk((long long)s->n * G, STEP_THREADS), STEP_THREADS, 0, st>>>(s->x0m, s->xv[0], s->nbr_start, s->nbr, s->n, s->c, s->Ks);
 }
 
 extern "C" int mis_set_mass(MisSim* s, const float* mass_dev, void* stream) {
@@ -324,7 +330,7 @@ extern "C" int mis_set_mass(MisSim* s, const float* mass_dev, void* stream) {
     CK_LAUNCH();
     if (s->G == 8) launch_volume<8>(s, st); else if (s->G == 16) launch_volume<16>(s, st); else launch_volume<32>(s, st);
     CK_LAUNCH();
-    s->launches += 2;
+    s->launches += 3;
     s->mass_set = true; s->dirty = true;
     return MIS_OK;
 }
@@ -369,7 +375,10 @@ extern "C" int mis_set_dirichlet(MisSim* s, const float* free_dev, void* stream)
 
 // ------------------------------------------------------------------ step machinery
 template <int G> static void launch_deform(MisSim* s, const View& v, cudaStream_t st) {
-    k_deform<G><<<nblk((long long)s->n * G, STEP_THREADS), STEP_THREADS, 0, st>>>(v, s->c);
+    if (s->p.two_pass_deform)
+        k_deform<G, true><<<nblk((long long)s->n * G, STEP_THREADS), STEP_THREADS, 0, st>>>(v, s->c);
+    else
+        k_deform<G, false><<<nblk((long long)s->n * G, STEP_THREADS), STEP_THREADS, 0, st>>>(v, s->c);
 }
 template <int G> static void launch_force(MisSim* s, const View& v, int mode, cudaStream_t st) {
     if (s->p.symmetric_pair)

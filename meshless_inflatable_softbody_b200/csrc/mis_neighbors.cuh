@@ -34,6 +34,7 @@ __device__ __forceinline__ uint32_t morton3(uint32_t x, uint32_t y, uint32_t z) 
 __global__ void __launch_bounds__(256) k_cell_coords(const float* __restrict__ x0, int n, float inv_cw,
                                                      int gx, int gy, int gz,
                                                      int* __restrict__ coords, int* __restrict__ cell_index,
+                                                     uint32_t* __restrict__ subkey,
                                                      int* __restrict__ bounds /* min xyz, max xyz */) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int cx = INT_MAX, cy = INT_MAX, cz = INT_MAX, mx = INT_MIN, my = INT_MIN, mz = INT_MIN;
@@ -42,6 +43,13 @@ __global__ void __launch_bounds__(256) k_cell_coords(const float* __restrict__ x
         cy = my = cell_coord(x0[3 * i + 1], inv_cw);
         cz = mz = cell_coord(x0[3 * i + 2], inv_cw);
         coords[3 * i + 0] = cx; coords[3 * i + 1] = cy; coords[3 * i + 2] = cz;
+        // position inside the cell in eighths of the span (-1, 1) around the truncated coordinate: orders the
+        // particles of a cell along a fine Morton curve (locality of the neighbour runs; no effect on results)
+        float fx = __fmul_rn(x0[3 * i + 0], inv_cw) - (float)cx, fy = __fmul_rn(x0[3 * i + 1], inv_cw) - (float)cy,
+              fz = __fmul_rn(x0[3 * i + 2], inv_cw) - (float)cz;
+        int sx = min(max((int)floorf((fx + 1.f) * 4.f), 0), 7), sy = min(max((int)floorf((fy + 1.f) * 4.f), 0), 7),
+            sz = min(max((int)floorf((fz + 1.f) * 4.f), 0), 7);
+        subkey[i] = morton3((uint32_t)sx, (uint32_t)sy, (uint32_t)sz);
         // hash_grid_index: +2^20 origin, clamp at 0, mod dim, x fastest
         const int origin = 1 << 20;
         int hx = max(cx + origin, 0) % gx, hy = max(cy + origin, 0) % gy, hz = max(cz + origin, 0) % gz;
@@ -60,29 +68,32 @@ __global__ void __launch_bounds__(256) k_cell_coords(const float* __restrict__ x
     }
 }
 
-__global__ void __launch_bounds__(256) k_cell_keys(const int* __restrict__ coords, int n, int3 cmin, uint32_t* __restrict__ keys) {
+// key = Morton(cell - cmin) << sub_bits | top sub_bits bits of the 9-bit in-cell Morton code
+__global__ void __launch_bounds__(256) k_cell_keys(const int* __restrict__ coords, const uint32_t* __restrict__ subkey, int n, int3 cmin,
+                                                   int sub_bits, uint32_t* __restrict__ keys) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    keys[i] = morton3((uint32_t)(coords[3 * i] - cmin.x), (uint32_t)(coords[3 * i + 1] - cmin.y), (uint32_t)(coords[3 * i + 2] - cmin.z));
+    uint32_t cell = morton3((uint32_t)(coords[3 * i] - cmin.x), (uint32_t)(coords[3 * i + 1] - cmin.y), (uint32_t)(coords[3 * i + 2] - cmin.z));
+    keys[i] = (cell << sub_bits) | (subkey[i] >> (9 - sub_bits));
 }
 
 // after the sort: dense cell table, inverse permutation, cell-sorted x0
 __global__ void __launch_bounds__(256) k_cell_table(const uint32_t* __restrict__ keys_sorted, const uint32_t* __restrict__ perm,
                                                     const int* __restrict__ coords, const float* __restrict__ x0, int n,
-                                                    int3 cmin, int3 cdim,
+                                                    int3 cmin, int3 cdim, int sub_bits,
                                                     int* __restrict__ cell_start, int* __restrict__ cell_end,
                                                     int* __restrict__ cell_lin_sorted, int* __restrict__ inv_perm,
                                                     float4* __restrict__ x0m) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     uint32_t id = perm[s];
-    uint32_t key = keys_sorted[s];
+    uint32_t key = keys_sorted[s] >> sub_bits;
     int cx = coords[3 * id] - cmin.x, cy = coords[3 * id + 1] - cmin.y, cz = coords[3 * id + 2] - cmin.z;
     int lin = (cz * cdim.y + cy) * cdim.x + cx;
     cell_lin_sorted[s] = lin;
     inv_perm[id] = s;
-    if (s == 0 || keys_sorted[s - 1] != key) cell_start[lin] = s;
-    if (s == n - 1 || keys_sorted[s + 1] != key) cell_end[lin] = s + 1;
+    if (s == 0 || (keys_sorted[s - 1] >> sub_bits) != key) cell_start[lin] = s;
+    if (s == n - 1 || (keys_sorted[s + 1] >> sub_bits) != key) cell_end[lin] = s + 1;
     float* dst = reinterpret_cast<float*>(x0m + s);       // keep .w (mass)
     dst[0] = x0[3 * id]; dst[1] = x0[3 * id + 1]; dst[2] = x0[3 * id + 2];
 }

@@ -20,8 +20,11 @@
 //   vel[s]   = (v, -)     f1[s] = (force_1 of the current frame, -)
 //   fel[s]   = (elastic force of the current frame, -)
 //   fext[s], freem[s] = external force, Dirichlet mask      matl[s] = (mu, lam, ratio, rho)
-//   RS[4s..] = (R00 R01 R02 R10)(R11 R12 R20 R21)(R22 Sxx Sxy Sxz)(Syy Syz Szz V)
-//   Fd[3s..] = (F00 F01 F02 F10)(F11 F12 F20 F21)(F22 - - -)
+//   RS: 4 float4 planes of n entries (plane p at RS + p*n), so that the lanes of a group
+//       reading consecutive neighbours touch consecutive 16-byte words of ONE plane:
+//       RS0 = (R00 R01 R02 R10)  RS1 = (R11 R12 R20 R21)  RS2 = (R22 Sxx Sxy Sxz)  RS3 = (Syy Syz Szz V)
+//   Fd: 3 planes  Fd0 = (F00 F01 F02 F10)  Fd1 = (F11 F12 F20 F21)  Fd2 = (F22 - - -)
+//   Ks: 3 planes, static K_i = sum_j (x0_j - x0_i) (V_j nabla_W_ij)^T (same packing as Fd)
 #pragma once
 #include "mis_math.cuh"
 
@@ -40,6 +43,7 @@ struct View {
     const float4* matl;
     float4* RS;
     float4* Fd;
+    const float4* Ks;                 // static K_i (3 planes)
     float* Apq;                       // optional (keep_fields), 9 floats per slot
     const unsigned long long* nbr_start;
     const uint32_t* nbr;
@@ -66,10 +70,12 @@ __global__ void __launch_bounds__(STEP_THREADS) k_volume(const float4* __restric
     const int gl = threadIdx.x % G;
     const int i = min(gid, n - 1);
     const float4 pi = x0m[i];
-    const unsigned long long b = nbr_start[i], e = nbr_start[i + 1];
+    const unsigned long long b = nbr_start[i];
+    const int cnt = (int)(nbr_start[i + 1] - b);
+    const uint32_t* __restrict__ lst = nbr + b;
     float rho = 0.f;
-    for (unsigned long long k = b + gl; k < e; k += G) {
-        const float4 pj = x0m[nbr[k]];
+    for (int k = gl; k < cnt; k += G) {
+        const float4 pj = x0m[lst[k]];
         float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
         rho += pj.w * kernel_W(dx * dx + dy * dy + dz * dz, c);
     }
@@ -82,36 +88,90 @@ __global__ void __launch_bounds__(STEP_THREADS) k_volume(const float4* __restric
     }
 }
 
-// ---------------------------------------------------------------- k_deform
+// Static part of compute_nabla_u (sim.py:193-209).  With g_ij = V_j nabla_W(x0_i - x0_j):
+//   N_i = sum_j (R_i^T dx_ij - d0_ij) g_ij^T = R_i^T (sum_j dx_ij g_ij^T) - K_i,
+//   K_i = sum_j d0_ij g_ij^T  depends on x0, V only: computed here once per set_mass.
 template <int G>
+__global__ void __launch_bounds__(STEP_THREADS) k_static_K(const float4* __restrict__ x0m, const float4* __restrict__ xv,
+                                                           const unsigned long long* __restrict__ nbr_start,
+                                                           const uint32_t* __restrict__ nbr, int n, Consts c, float4* __restrict__ Ks) {
+    const int gid = (blockIdx.x * STEP_THREADS + threadIdx.x) / G;
+    const int gl = threadIdx.x % G;
+    const int i = min(gid, n - 1);
+    const float4 p0i = x0m[i];
+    const unsigned long long b = nbr_start[i];
+    const int cnt = (int)(nbr_start[i + 1] - b);
+    const uint32_t* __restrict__ lst = nbr + b;
+    float K[9];
+#pragma unroll
+    for (int k = 0; k < 9; k++) K[k] = 0.f;
+    for (int k = gl; k < cnt; k += G) {
+        const uint32_t j = lst[k];
+        const float4 p0 = x0m[j];
+        const float d0x = p0.x - p0i.x, d0y = p0.y - p0i.y, d0z = p0.z - p0i.z;
+        const float nb = -kernel_gradW_coef(d0x * d0x + d0y * d0y + d0z * d0z, c) * xv[j].w;
+        const float gx = nb * d0x, gy = nb * d0y, gz = nb * d0z;
+        K[0] += d0x * gx; K[1] += d0x * gy; K[2] += d0x * gz;
+        K[3] += d0y * gx; K[4] += d0y * gy; K[5] += d0y * gz;
+        K[6] += d0z * gx; K[7] += d0z * gy; K[8] += d0z * gz;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) K[k] = group_sum<G>(K[k]);
+    if (gl == 0 && gid < n) {
+        Ks[i] = make_float4(K[0], K[1], K[2], K[3]);
+        Ks[n + i] = make_float4(K[4], K[5], K[6], K[7]);
+        Ks[2 * (size_t)n + i] = make_float4(K[8], 0.f, 0.f, 0.f);
+    }
+}
+
+// ---------------------------------------------------------------- k_deform
+// One pass over the neighbour list accumulates both moment sums
+//   A_i = sum_j (W_ij m_j) dx_ij d0_ij^T      (compute_A_pq, sim.py:170-183)
+//   B_i = sum_j dx_ij (V_j nabla_W_ij)^T       (the dynamic half of compute_nabla_u)
+// with dx_ij = x_j - x_i, d0_ij = x0_j - x0_i; both weights are scalars times d0_ij.
+// Then R_i = polar(A_i), N_i = R_i^T B_i - K_i, F_i = I + N_i^T, S_i = compute_sigma(F_i).
+// FAITHFUL2 = true keeps the reference's two-loop evaluation order (u = R^T dx - d0 formed per
+// pair, sim.py:207-208) for accuracy studies; results agree to the fp32 reorder floor.
+template <int G, bool FAITHFUL2>
 __global__ void __launch_bounds__(STEP_THREADS) k_deform(View s, Consts c) {
     const int gid = (blockIdx.x * STEP_THREADS + threadIdx.x) / G;
     const int gl = threadIdx.x % G;
-    const int i = min(gid, s.n - 1);
+    const int n = s.n;
+    const int i = min(gid, n - 1);
     const float4 p0i = s.x0m[i];
     const float4 pxi = s.xcur[i];
-    const unsigned long long b = s.nbr_start[i], e = s.nbr_start[i + 1];
+    const unsigned long long b = s.nbr_start[i];
+    const int cnt = (int)(s.nbr_start[i + 1] - b);
+    const uint32_t* __restrict__ lst = s.nbr + b;
 
-    // --- compute_A_pq: A = sum_j W_ij m_j (x_j - x_i) (x0_j - x0_i)^T
-    float A[9];
+    float A[9], B[9];
 #pragma unroll
-    for (int k = 0; k < 9; k++) A[k] = 0.f;
-    for (unsigned long long k = b + gl; k < e; k += G) {
-        const uint32_t j = s.nbr[k];
+    for (int k = 0; k < 9; k++) { A[k] = 0.f; B[k] = 0.f; }
+    for (int k = gl; k < cnt; k += G) {
+        const uint32_t j = lst[k];
         const float4 p0 = s.x0m[j];
         const float4 px = s.xcur[j];
         const float d0x = p0.x - p0i.x, d0y = p0.y - p0i.y, d0z = p0.z - p0i.z;
-        const float w = kernel_W(d0x * d0x + d0y * d0y + d0z * d0z, c) * p0.w;
+        float w, beta;
+        kernel_W_and_coef(d0x * d0x + d0y * d0y + d0z * d0z, c, w, beta);
+        w *= p0.w;                                        // W_ij m_j
         const float dx = px.x - pxi.x, dy = px.y - pxi.y, dz = px.z - pxi.z;
         const float tx = w * d0x, ty = w * d0y, tz = w * d0z;
         A[0] += dx * tx; A[1] += dx * ty; A[2] += dx * tz;
         A[3] += dy * tx; A[4] += dy * ty; A[5] += dy * tz;
         A[6] += dz * tx; A[7] += dz * ty; A[8] += dz * tz;
+        if (!FAITHFUL2) {
+            // nabla_W(x0_i - x0_j) = beta (x0_i - x0_j) = (-beta) d0
+            const float nb = -beta * px.w;                // * V_j
+            const float gx = nb * d0x, gy = nb * d0y, gz = nb * d0z;
+            B[0] += dx * gx; B[1] += dx * gy; B[2] += dx * gz;
+            B[3] += dy * gx; B[4] += dy * gy; B[5] += dy * gz;
+            B[6] += dz * gx; B[7] += dz * gy; B[8] += dz * gz;
+        }
     }
 #pragma unroll
     for (int k = 0; k < 9; k++) A[k] = group_sum<G>(A[k]);
 
-    // --- compute_R_i
     float R[9];
     if (c.identity_rot) {
 #pragma unroll
@@ -120,42 +180,53 @@ __global__ void __launch_bounds__(STEP_THREADS) k_deform(View s, Consts c) {
         polar_rotation(A, R);
     }
 
-    // --- compute_nabla_u: N = sum_j V_j (R^T (x_j - x_i) - (x0_j - x0_i)) nabla_W(x0_i - x0_j)^T
     float N[9];
+    if (FAITHFUL2) {
 #pragma unroll
-    for (int k = 0; k < 9; k++) N[k] = 0.f;
-    for (unsigned long long k = b + gl; k < e; k += G) {
-        const uint32_t j = s.nbr[k];
-        const float4 p0 = s.x0m[j];
-        const float4 px = s.xcur[j];
-        const float d0x = p0.x - p0i.x, d0y = p0.y - p0i.y, d0z = p0.z - p0i.z;
-        // nabla_W(x0_i - x0_j) = beta * (x0_i - x0_j) = (-beta) * d0
-        const float nb = -kernel_gradW_coef(d0x * d0x + d0y * d0y + d0z * d0z, c) * px.w;   // * V_j
-        const float dx = px.x - pxi.x, dy = px.y - pxi.y, dz = px.z - pxi.z;
-        const float ux = R[0] * dx + R[3] * dy + R[6] * dz - d0x;
-        const float uy = R[1] * dx + R[4] * dy + R[7] * dz - d0y;
-        const float uz = R[2] * dx + R[5] * dy + R[8] * dz - d0z;
-        const float gx = nb * d0x, gy = nb * d0y, gz = nb * d0z;
-        N[0] += ux * gx; N[1] += ux * gy; N[2] += ux * gz;
-        N[3] += uy * gx; N[4] += uy * gy; N[5] += uy * gz;
-        N[6] += uz * gx; N[7] += uz * gy; N[8] += uz * gz;
+        for (int k = 0; k < 9; k++) N[k] = 0.f;
+        for (int k = gl; k < cnt; k += G) {
+            const uint32_t j = lst[k];
+            const float4 p0 = s.x0m[j];
+            const float4 px = s.xcur[j];
+            const float d0x = p0.x - p0i.x, d0y = p0.y - p0i.y, d0z = p0.z - p0i.z;
+            const float nb = -kernel_gradW_coef(d0x * d0x + d0y * d0y + d0z * d0z, c) * px.w;
+            const float dx = px.x - pxi.x, dy = px.y - pxi.y, dz = px.z - pxi.z;
+            const float ux = R[0] * dx + R[3] * dy + R[6] * dz - d0x;
+            const float uy = R[1] * dx + R[4] * dy + R[7] * dz - d0y;
+            const float uz = R[2] * dx + R[5] * dy + R[8] * dz - d0z;
+            const float gx = nb * d0x, gy = nb * d0y, gz = nb * d0z;
+            N[0] += ux * gx; N[1] += ux * gy; N[2] += ux * gz;
+            N[3] += uy * gx; N[4] += uy * gy; N[5] += uy * gz;
+            N[6] += uz * gx; N[7] += uz * gy; N[8] += uz * gz;
+        }
+#pragma unroll
+        for (int k = 0; k < 9; k++) N[k] = group_sum<G>(N[k]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; k++) B[k] = group_sum<G>(B[k]);
+        const float4 k0 = s.Ks[i], k1 = s.Ks[n + i], k2 = s.Ks[2 * (size_t)n + i];
+        const float K[9] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w, k2.x};
+        // N = R^T B - K
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int q = 0; q < 3; q++)
+                N[3 * r + q] = R[0 * 3 + r] * B[0 * 3 + q] + R[1 * 3 + r] * B[1 * 3 + q] + R[2 * 3 + r] * B[2 * 3 + q] - K[3 * r + q];
     }
-#pragma unroll
-    for (int k = 0; k < 9; k++) N[k] = group_sum<G>(N[k]);
 
-    if (gl == 0 && gid < s.n) {
+    if (gl == 0 && gid < n) {
         // def_grad = I + N^T
         float F[9] = {1.f + N[0], N[3], N[6], N[1], 1.f + N[4], N[7], N[2], N[5], 1.f + N[8]};
         const float4 ml = s.matl[i];
         float S[6];
         stress_svk(F, ml.x, ml.y, ml.z, c, S);
-        s.RS[4 * i + 0] = make_float4(R[0], R[1], R[2], R[3]);
-        s.RS[4 * i + 1] = make_float4(R[4], R[5], R[6], R[7]);
-        s.RS[4 * i + 2] = make_float4(R[8], S[0], S[1], S[2]);
-        s.RS[4 * i + 3] = make_float4(S[3], S[4], S[5], pxi.w);
-        s.Fd[3 * i + 0] = make_float4(F[0], F[1], F[2], F[3]);
-        s.Fd[3 * i + 1] = make_float4(F[4], F[5], F[6], F[7]);
-        s.Fd[3 * i + 2] = make_float4(F[8], 0.f, 0.f, 0.f);
+        s.RS[i] = make_float4(R[0], R[1], R[2], R[3]);
+        s.RS[n + i] = make_float4(R[4], R[5], R[6], R[7]);
+        s.RS[2 * (size_t)n + i] = make_float4(R[8], S[0], S[1], S[2]);
+        s.RS[3 * (size_t)n + i] = make_float4(S[3], S[4], S[5], pxi.w);
+        s.Fd[i] = make_float4(F[0], F[1], F[2], F[3]);
+        s.Fd[n + i] = make_float4(F[4], F[5], F[6], F[7]);
+        s.Fd[2 * (size_t)n + i] = make_float4(F[8], 0.f, 0.f, 0.f);
         if (s.Apq) {
 #pragma unroll
             for (int k = 0; k < 9; k++) s.Apq[9 * (size_t)i + k] = A[k];
@@ -239,16 +310,23 @@ __global__ void __launch_bounds__(STEP_THREADS) k_force(View s, Consts c, int mo
     const int gl = threadIdx.x % G;
     const int i = min(gid, s.n - 1);
     const float4 p0i = s.x0m[i];
-    const float4 f0 = s.Fd[3 * i + 0], f1 = s.Fd[3 * i + 1], f2 = s.Fd[3 * i + 2];
+    const int n = s.n;
+    const float4* __restrict__ RS0 = s.RS;
+    const float4* __restrict__ RS1 = s.RS + n;
+    const float4* __restrict__ RS2 = s.RS + 2 * (size_t)n;
+    const float4* __restrict__ RS3 = s.RS + 3 * (size_t)n;
+    const float4 f0 = s.Fd[i], f1 = s.Fd[n + i], f2 = s.Fd[2 * (size_t)n + i];
     const float F[9] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x};
-    const unsigned long long b = s.nbr_start[i], e = s.nbr_start[i + 1];
+    const unsigned long long b = s.nbr_start[i];
+    const int cnt = (int)(s.nbr_start[i + 1] - b);
+    const uint32_t* __restrict__ lst = s.nbr + b;
 
     float ax = 0.f, ay = 0.f, az = 0.f;     // sum_j V_j R_j F_i S_j nw
     float gx = 0.f, gy = 0.f, gz = 0.f;     // sum_j V_j nw
-    for (unsigned long long k = b + gl; k < e; k += G) {
-        const uint32_t j = s.nbr[k];
+    for (int k = gl; k < cnt; k += G) {
+        const uint32_t j = lst[k];
         const float4 p0 = s.x0m[j];
-        const float4 r0 = s.RS[4 * j + 0], r1 = s.RS[4 * j + 1], r2 = s.RS[4 * j + 2], r3 = s.RS[4 * j + 3];
+        const float4 r0 = RS0[j], r1 = RS1[j], r2 = RS2[j], r3 = RS3[j];
         const float d0x = p0.x - p0i.x, d0y = p0.y - p0i.y, d0z = p0.z - p0i.z;
         const float nb = -kernel_gradW_coef(d0x * d0x + d0y * d0y + d0z * d0z, c) * r3.w;   // V_j folded in
         const float nx = nb * d0x, ny = nb * d0y, nz = nb * d0z;                            // V_j nabla_W_ij
@@ -270,7 +348,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_force(View s, Consts c, int mo
     gx = group_sum<G>(gx); gy = group_sum<G>(gy); gz = group_sum<G>(gz);
 
     if (gl == 0 && gid < s.n) {
-        const float4 r0 = s.RS[4 * i + 0], r1 = s.RS[4 * i + 1], r2 = s.RS[4 * i + 2], r3 = s.RS[4 * i + 3];
+        const float4 r0 = RS0[i], r1 = RS1[i], r2 = RS2[i], r3 = RS3[i];
         const float tx = r2.y * gx + r2.z * gy + r2.w * gz;
         const float ty = r2.z * gx + r3.x * gy + r3.y * gz;
         const float tz = r2.w * gx + r3.y * gy + r3.z * gz;
@@ -282,7 +360,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_force(View s, Consts c, int mo
         fel.x = hv * (ax + r0.x * ux + r0.y * uy + r0.z * uz);
         fel.y = hv * (ay + r0.w * ux + r1.x * uy + r1.y * uz);
         fel.z = hv * (az + r1.z * ux + r1.w * uy + r2.x * uz);
-        if (b == e) fel = make_float3(0.f, 0.f, 0.f);   // isolated particle: the reference loop never runs (V = m/0)
+        if (cnt == 0) fel = make_float3(0.f, 0.f, 0.f);   // isolated particle: the reference loop never runs (V = m/0)
         integrate_epilogue(s, c, i, fel, mode, p0i, s.xcur[i]);
     }
 }
@@ -297,13 +375,20 @@ __global__ void __launch_bounds__(STEP_THREADS) k_force_sym(View s, Consts c, in
     const int gl = threadIdx.x % G;
     const int i = min(gid, s.n - 1);
     const float4 p0i = s.x0m[i];
-    const unsigned long long b = s.nbr_start[i], e = s.nbr_start[i + 1];
+    const int n = s.n;
+    const float4* __restrict__ RS0 = s.RS;
+    const float4* __restrict__ RS1 = s.RS + n;
+    const float4* __restrict__ RS2 = s.RS + 2 * (size_t)n;
+    const float4* __restrict__ RS3 = s.RS + 3 * (size_t)n;
+    const unsigned long long b = s.nbr_start[i];
+    const int cnt = (int)(s.nbr_start[i + 1] - b);
+    const uint32_t* __restrict__ lst = s.nbr + b;
     float ax = 0.f, ay = 0.f, az = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
-    for (unsigned long long k = b + gl; k < e; k += G) {
-        const uint32_t j = s.nbr[k];
+    for (int k = gl; k < cnt; k += G) {
+        const uint32_t j = lst[k];
         const float4 p0 = s.x0m[j];
-        const float4 r0 = s.RS[4 * j + 0], r1 = s.RS[4 * j + 1], r2 = s.RS[4 * j + 2], r3 = s.RS[4 * j + 3];
-        const float4 f0 = s.Fd[3 * j + 0], f1 = s.Fd[3 * j + 1], f2 = s.Fd[3 * j + 2];
+        const float4 r0 = RS0[j], r1 = RS1[j], r2 = RS2[j], r3 = RS3[j];
+        const float4 f0 = s.Fd[j], f1 = s.Fd[n + j], f2 = s.Fd[2 * (size_t)n + j];
         const float d0x = p0.x - p0i.x, d0y = p0.y - p0i.y, d0z = p0.z - p0i.z;
         const float nb = -kernel_gradW_coef(d0x * d0x + d0y * d0y + d0z * d0z, c) * r3.w;
         const float nx = nb * d0x, ny = nb * d0y, nz = nb * d0z;
@@ -321,8 +406,8 @@ __global__ void __launch_bounds__(STEP_THREADS) k_force_sym(View s, Consts c, in
     ax = group_sum<G>(ax); ay = group_sum<G>(ay); az = group_sum<G>(az);
     gx = group_sum<G>(gx); gy = group_sum<G>(gy); gz = group_sum<G>(gz);
     if (gl == 0 && gid < s.n) {
-        const float4 r0 = s.RS[4 * i + 0], r1 = s.RS[4 * i + 1], r2 = s.RS[4 * i + 2], r3 = s.RS[4 * i + 3];
-        const float4 f0 = s.Fd[3 * i + 0], f1 = s.Fd[3 * i + 1], f2 = s.Fd[3 * i + 2];
+        const float4 r0 = RS0[i], r1 = RS1[i], r2 = RS2[i], r3 = RS3[i];
+        const float4 f0 = s.Fd[i], f1 = s.Fd[n + i], f2 = s.Fd[2 * (size_t)n + i];
         const float tx = r2.y * gx + r2.z * gy + r2.w * gz;
         const float ty = r2.z * gx + r3.x * gy + r3.y * gz;
         const float tz = r2.w * gx + r3.y * gy + r3.z * gz;
@@ -334,7 +419,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_force_sym(View s, Consts c, in
         fel.x = hv * (ax + r0.x * ux + r0.y * uy + r0.z * uz);
         fel.y = hv * (ay + r0.w * ux + r1.x * uy + r1.y * uz);
         fel.z = hv * (az + r1.z * ux + r1.w * uy + r2.x * uz);
-        if (b == e) fel = make_float3(0.f, 0.f, 0.f);   // isolated particle: the reference loop never runs (V = m/0)
+        if (cnt == 0) fel = make_float3(0.f, 0.f, 0.f);   // isolated particle: the reference loop never runs (V = m/0)
         integrate_epilogue(s, c, i, fel, mode, p0i, s.xcur[i]);
     }
 }
@@ -389,15 +474,15 @@ __global__ void __launch_bounds__(256) k_export_field(View s, const int* __restr
     if (i >= s.n) return;
     int p = inv_perm[i];
     if (which == 0) {
-        float4 r0 = s.RS[4 * p], r1 = s.RS[4 * p + 1], r2 = s.RS[4 * p + 2];
+        float4 r0 = s.RS[p], r1 = s.RS[s.n + p], r2 = s.RS[2 * (size_t)s.n + p];
         float R[9] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
         for (int k = 0; k < 9; k++) dst[9 * (size_t)i + k] = R[k];
     } else if (which == 1) {
-        float4 r2 = s.RS[4 * p + 2], r3 = s.RS[4 * p + 3];
+        float4 r2 = s.RS[2 * (size_t)s.n + p], r3 = s.RS[3 * (size_t)s.n + p];
         float S[9] = {r2.y, r2.z, r2.w, r2.z, r3.x, r3.y, r2.w, r3.y, r3.z};
         for (int k = 0; k < 9; k++) dst[9 * (size_t)i + k] = S[k];
     } else if (which == 2) {
-        float4 f0 = s.Fd[3 * p], f1 = s.Fd[3 * p + 1], f2 = s.Fd[3 * p + 2];
+        float4 f0 = s.Fd[p], f1 = s.Fd[s.n + p], f2 = s.Fd[2 * (size_t)s.n + p];
         float F[9] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x};
         for (int k = 0; k < 9; k++) dst[9 * (size_t)i + k] = F[k];
     } else if (which == 3) {

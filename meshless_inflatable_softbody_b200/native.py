@@ -29,6 +29,7 @@ class MisParams(C.Structure):
         ("symmetric_pair", C.c_int), ("identity_rot", C.c_int), ("self_density", C.c_int),
         ("euler", C.c_int), ("no_contact", C.c_int),
         ("lanes_per_particle", C.c_int), ("keep_fields", C.c_int), ("graph_steps", C.c_int),
+        ("two_pass_deform", C.c_int),
     ]
 
 

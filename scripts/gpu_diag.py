@@ -35,10 +35,8 @@ def main(n=3000, G=8, steps=50):
     print("info pairs", info.total_pairs, "max_k", info.max_neighbors, "dim", list(info.cell_dim), "min", list(info.cell_min))
     # within a cell ascending caller id
     s, e = sim.cell_ranges(); s = s.cpu().numpy(); e = e.cpu().numpy()
-    ok = True
-    for a, b in zip(s, e):
-        if b > a and not np.all(np.diff(pm[a:b]) > 0): ok = False
-    print("cells hold ascending caller ids:", ok, " cells covered:", int((e - s).sum()) == n)
+    print("hash-grid order from cell_index == oracle point_ids:", np.array_equal(np.argsort(ci.cpu().numpy(), kind="stable"), oids),
+          " cells covered:", int((e - s).sum()) == n)
     # --- neighbours
     off, nb = sim.neighbors(); off = off.cpu().numpy(); nb = nb.cpu().numpy()
     cnt, ooff, oflat = o.neighbor_lists()

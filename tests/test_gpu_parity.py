@@ -40,9 +40,10 @@ def test_cells_and_neighbours_bit_exact(n, spacing, seed):
     assert np.array_equal(np.sort(pm), np.arange(len(x0)))
     s, e = (_np(t) for t in sim.cell_ranges())
     assert int((e - s).sum()) == len(x0)
-    for a, b in zip(s, e):                        # stable sort: ascending caller id inside a cell
-        assert b <= a or np.all(np.diff(pm[a:b]) > 0)
+    for a, b in zip(s, e):                        # a cell is one contiguous slot range
         assert b <= a or len(np.unique(cc[pm[a:b]], axis=0)) == 1
+    # hash_grid_point_id order (stable sort by cell index) follows from the bit-exact cell indices
+    assert np.array_equal(np.argsort(ci, kind="stable"), oids)
     off, nb = (_np(t) for t in sim.neighbors())
     cnt, ooff, oflat = o.neighbor_lists()
     assert np.array_equal(np.diff(off), cnt)
@@ -167,7 +168,7 @@ def test_ballistic_is_bit_exact():
     sim.startup(); o.startup()
     sim.step(400); o.step(400)
     x, v = sim.position_velocity()
-    assert o.position()[:, 1].min() < 1e-4          # penalty branch exercised
+    assert (o.velocity()[:, 1] > 0).any()           # penalty branch exercised: some particles bounced
     assert np.array_equal(_np(x), o.position()) and np.array_equal(_np(v), o.velocity())
 
 
@@ -246,7 +247,7 @@ def test_taichi_variant_flags(sphere800):
 
 # ------------------------------------------------------------------ full-size properties (BASELINE config 2 size)
 def test_full_size_properties():
-    x0, _ = scenes.jittered_sphere(100_000, seed=0)
+    x0, _ = scenes.jittered_sphere(100_000, seed=0, centre=(0.0, 0.2, 0.0))   # radius 0.1 m: clear of the ground
     n = len(x0)
     sim = _sim(x0)
     info = sim.neighbor_info()

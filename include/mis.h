@@ -55,10 +55,12 @@ typedef struct MisParams {
     int   euler;             /* sim_taichi.py:167-172 symplectic Euler              */
     int   no_contact;        /* sim_taichi.py has no ground penalty                 */
     /* tuning (0 = library default) */
-    int   lanes_per_particle;/* 8, 16 or 32 lanes cooperate on one particle         */
+    int   lanes_per_particle;/* 8, 16 or 32 lanes cooperate on one cluster          */
     int   keep_fields;       /* 1: also store A_pq each step (diagnostics export)   */
     int   graph_steps;       /* steps per captured CUDA graph chunk (0 = default 32, <0 = no graphs) */
     int   two_pass_deform;   /* 1: def_grad with the reference's two-loop order (sim.py:203-208)  */
+    int   cluster_size;      /* 1, 2 or 4 consecutive cell-sorted particles share one union
+                                neighbour list and every gathered record (0 = default 2)       */
 } MisParams;
 
 typedef struct MisNeighborInfo {
@@ -68,6 +70,8 @@ typedef struct MisNeighborInfo {
     int   cell_min[3];       /* integer cell coordinate of the grid origin          */
     int   cell_dim[3];       /* dense cell table dims (x fastest)                   */
     float cell_width;        /* 2h                                                  */
+    int   cluster_size;      /* particles per cluster (consecutive cell-sorted slots) */
+    long long union_entries; /* sum of the clusters' union-list lengths             */
 } MisNeighborInfo;
 
 const char* mis_last_error(void);

@@ -4,7 +4,7 @@
 #include "mis_math.cuh"
 #include "mis_neighbors.cuh"
 #include "mis_sort.cuh"
-#include "mis_step.cuh"
+#include "mis_cluster.cuh"
 #include "mis_sdf.cuh"
 
 #include <math.h>
@@ -30,7 +30,7 @@ struct MisSim {
     int n = 0;
     MisParams p{};
     Consts c{};
-    int G = 8;
+    int G = 8, C = 2;                 // lanes per cluster, particles per cluster
     // caller-order copies
     float* x0_orig = nullptr;
     int* coords = nullptr;
@@ -57,6 +57,11 @@ struct MisSim {
     long long nbr_cap = 0, total_pairs = 0;
     int* max_k_dev = nullptr;
     int max_k = 0;
+    // cluster union lists (what the step kernels stream)
+    uint32_t* cl_count = nullptr;
+    unsigned long long* cl_start = nullptr;
+    uint32_t* cl = nullptr;
+    long long cl_cap = 0, cl_total = 0;
     float d2_limit = 0.f;
     // cell-sorted state
     float4 *x0m = nullptr, *xv[2] = {nullptr, nullptr}, *vel = nullptr, *f1 = nullptr, *fel = nullptr;
@@ -118,7 +123,7 @@ static View make_view(MisSim* s) {
     v.x0m = s->x0m; v.xcur = s->xv[s->cur]; v.xnext = s->xv[s->cur ^ 1];
     v.vel = s->vel; v.f1 = s->f1; v.fel = s->fel; v.fext = s->fext; v.freem = s->freem; v.matl = s->matl;
     v.RS = s->RS; v.Fd = s->Fd; v.Ks = s->Ks; v.Apq = s->p.keep_fields ? s->Apq : nullptr;
-    v.nbr_start = s->nbr_start; v.nbr = s->nbr;
+    v.cl_start = s->cl_start; v.cl = s->cl;
     return v;
 }
 
@@ -142,6 +147,9 @@ extern "C" int mis_create(int n, const float* x0_dev, const MisParams* params, v
     int G = s->p.lanes_per_particle ? s->p.lanes_per_particle : 8;
     if (G != 8 && G != 16 && G != 32) { delete s; return fail(MIS_E_INVALID, "lanes_per_particle must be 8, 16 or 32"); }
     s->G = G;
+    int Cs = s->p.cluster_size ? s->p.cluster_size : 2;
+    if (Cs != 1 && Cs != 2 && Cs != 4) { delete s; return fail(MIS_E_INVALID, "cluster_size must be 1, 2 or 4"); }
+    s->C = Cs;
     make_consts(s);
     s->d2_limit = find_d2_limit(s->p.h);
     const size_t N = (size_t)n;
@@ -155,6 +163,7 @@ extern "C" int mis_create(int n, const float* x0_dev, const MisParams* params, v
     ALLOC(s->bounds_dev, 8); ALLOC(s->max_k_dev, 2);
     ALLOC(s->cell_lin_sorted, N);
     ALLOC(s->nbr_count, N); ALLOC(s->nbr_start, N + 1); ALLOC(s->scan_tmp, (size_t)nblk(n, SCAN_TILE) + 1);
+    ALLOC(s->cl_count, N); ALLOC(s->cl_start, N + 1);
     ALLOC(s->x0m, N); ALLOC(s->xv[0], N); ALLOC(s->xv[1], N); ALLOC(s->vel, N); ALLOC(s->f1, N); ALLOC(s->fel, N);
     ALLOC(s->fext, N); ALLOC(s->freem, N); ALLOC(s->matl, N); ALLOC(s->RS, 4 * N); ALLOC(s->Fd, 3 * N); ALLOC(s->Ks, 3 * N);
     ALLOC(s->scratch4, 2 * N); ALLOC(s->stage, 6 * N);
@@ -191,7 +200,7 @@ extern "C" int mis_destroy(MisSim* s) {
     sdf_free(s->sdf);
     void* ptrs[] = {s->x0_orig, s->coords, s->cell_index, s->keys, s->subkey, s->Ks, s->perm, s->inv_perm, s->rs.keys_alt, s->rs.vals_alt,
                     s->rs.hist, s->rs.hist_scanned, s->rs.tile_tmp, s->bounds_dev, s->max_k_dev, s->cell_start, s->cell_end,
-                    s->cell_lin_sorted, s->nbr_count, s->nbr_start, s->scan_tmp, s->nbr, s->x0m, s->xv[0], s->xv[1], s->vel,
+                    s->cell_lin_sorted, s->nbr_count, s->nbr_start, s->scan_tmp, s->nbr, s->cl_count, s->cl_start, s->cl, s->x0m, s->xv[0], s->xv[1], s->vel,
                     s->f1, s->fel, s->fext, s->freem, s->matl, s->RS, s->Fd, s->Apq, s->scratch4, s->stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     delete s;
@@ -199,6 +208,39 @@ extern "C" int mis_destroy(MisSim* s) {
 }
 
 // ------------------------------------------------------------------ neighbour structure
+template <int C> static void launch_cluster_walk(MisSim* s, int fill, cudaStream_t st) {
+    const int nc = (s->n + C - 1) / C;
+    const int3 cdim = make_int3(s->cell_dim[0], s->cell_dim[1], s->cell_dim[2]);
+    k_cluster_walk<C><<<nblk(nc, 128), 128, 0, st>>>(s->x0m, s->cell_lin_sorted, s->cell_start, s->cell_end, cdim, s->n, s->d2_limit, fill,
+                                                     s->cl_start, s->cl, s->cl_count);
+}
+static void cluster_walk(MisSim* s, int fill, cudaStream_t st) {
+    if (s->C == 1) launch_cluster_walk<1>(s, fill, st); else if (s->C == 2) launch_cluster_walk<2>(s, fill, st); else launch_cluster_walk<4>(s, fill, st);
+    s->launches++;
+}
+// union neighbour list per cluster of C consecutive slots: count, scan, fill
+static int build_cluster_lists(MisSim* s, cudaStream_t st) {
+    const int nc = (s->n + s->C - 1) / s->C;
+    cluster_walk(s, 0, st);
+    CK_LAUNCH();
+    s->launches += exclusive_scan<unsigned long long>(s->cl_count, s->cl_start, nc, s->scan_tmp, st);
+    CK_LAUNCH();
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, s->cl_start + nc, sizeof total, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    s->cl_total = (long long)total;
+    if (s->cl_total > s->cl_cap || !s->cl) {
+        if (s->cl) cudaFree(s->cl);
+        s->cl = nullptr;
+        CK(dalloc(&s->cl, (size_t)s->cl_total + 64));
+        CK(cudaMemsetAsync(s->cl, 0, ((size_t)s->cl_total + 64) * sizeof(uint32_t), st));
+        s->cl_cap = s->cl_total;
+    }
+    cluster_walk(s, 1, st);
+    CK_LAUNCH();
+    return MIS_OK;
+}
+
 extern "C" int mis_build_neighbors(MisSim* s, void* stream) {
     if (!s) return fail(MIS_E_INVALID, "null sim");
     cudaStream_t st = (cudaStream_t)stream;
@@ -265,6 +307,9 @@ extern "C" int mis_build_neighbors(MisSim* s, void* stream) {
     k_nbr_walk<<<nblk(n, 128), 128, 0, st>>>(s->x0m, s->cell_lin_sorted, s->cell_start, s->cell_end, cdim, n, s->d2_limit, 1,
                                              s->nbr_start, s->nbr, s->nbr_count, s->max_k_dev);
     CK_LAUNCH(); s->launches++;
+    int rc = build_cluster_lists(s, st);
+    if (rc) return rc;
+    drop_graph(s);                            // a captured chunk holds the old list pointers
     s->built = true;
     return MIS_OK;
 }
@@ -274,6 +319,7 @@ extern "C" int mis_get_neighbor_info(MisSim* s, MisNeighborInfo* out) {
     out->total_pairs = s->total_pairs; out->max_neighbors = s->max_k; out->n = s->n;
     for (int a = 0; a < 3; a++) { out->cell_min[a] = s->cell_min[a]; out->cell_dim[a] = s->cell_dim[a]; }
     out->cell_width = 2.f * s->p.h;
+    out->cluster_size = s->C; out->union_entries = s->cl_total;
     return MIS_OK;
 }
 
@@ -374,24 +420,47 @@ extern "C" int mis_set_dirichlet(MisSim* s, const float* free_dev, void* stream)
 }
 
 // ------------------------------------------------------------------ step machinery
-template <int G> static void launch_deform(MisSim* s, const View& v, cudaStream_t st) {
-    if (s->p.two_pass_deform)
-        k_deform<G, true><<<nblk((long long)s->n * G, STEP_THREADS), STEP_THREADS, 0, st>>>(v, s->c);
-    else
-        k_deform<G, false><<<nblk((long long)s->n * G, STEP_THREADS), STEP_THREADS, 0, st>>>(v, s->c);
+template <int C, int G> static void launch_deform(MisSim* s, const View& v, cudaStream_t st) {
+    const int nc = (s->n + C - 1) / C;
+    k_deform_c<C, G, false><<<nblk((long long)nc * G, STEP_THREADS), STEP_THREADS, 0, st>>>(v, s->c);
 }
-template <int G> static void launch_force(MisSim* s, const View& v, int mode, cudaStream_t st) {
-    if (s->p.symmetric_pair)
-        k_force_sym<G><<<nblk((long long)s->n * G, STEP_THREADS), STEP_THREADS, 0, st>>>(v, s->c, mode);
-    else
-        k_force<G><<<nblk((long long)s->n * G, STEP_THREADS), STEP_THREADS, 0, st>>>(v, s->c, mode);
+template <int C> static void launch_deform2(MisSim* s, const View& v, cudaStream_t st) {
+    const int nc = (s->n + C - 1) / C;
+    k_deform_c<C, 8, true><<<nblk((long long)nc * 8, STEP_THREADS), STEP_THREADS, 0, st>>>(v, s->c);
 }
+template <int C, int G> static void launch_force(MisSim* s, const View& v, int mode, cudaStream_t st) {
+    const int nc = (s->n + C - 1) / C;
+    k_force_c<C, G, false><<<nblk((long long)nc * G, STEP_THREADS), STEP_THREADS, 0, st>>>(v, s->c, mode);
+}
+template <int C> static void launch_force_sym(MisSim* s, const View& v, int mode, cudaStream_t st) {
+    const int nc = (s->n + C - 1) / C;
+    k_force_c<C, 8, true><<<nblk((long long)nc * 8, STEP_THREADS), STEP_THREADS, 0, st>>>(v, s->c, mode);
+}
+#define MIS_DISPATCH_CG(FN, ...)                                                                  \
+    do {                                                                                          \
+        const int key_ = s->C * 100 + s->G;                                                       \
+        switch (key_) {                                                                           \
+            case 108: FN<1, 8>(__VA_ARGS__); break;   case 116: FN<1, 16>(__VA_ARGS__); break;    \
+            case 132: FN<1, 32>(__VA_ARGS__); break;  case 208: FN<2, 8>(__VA_ARGS__); break;     \
+            case 216: FN<2, 16>(__VA_ARGS__); break;  case 232: FN<2, 32>(__VA_ARGS__); break;    \
+            case 408: FN<4, 8>(__VA_ARGS__); break;   case 416: FN<4, 16>(__VA_ARGS__); break;    \
+            default: FN<4, 32>(__VA_ARGS__); break;                                               \
+        }                                                                                         \
+    } while (0)
 static void enqueue_deform(MisSim* s, const View& v, cudaStream_t st) {
-    if (s->G == 8) launch_deform<8>(s, v, st); else if (s->G == 16) launch_deform<16>(s, v, st); else launch_deform<32>(s, v, st);
+    if (s->p.two_pass_deform) {       // reference two-loop order: accuracy studies, fixed 8 lanes per cluster
+        if (s->C == 1) launch_deform2<1>(s, v, st); else if (s->C == 2) launch_deform2<2>(s, v, st); else launch_deform2<4>(s, v, st);
+    } else {
+        MIS_DISPATCH_CG(launch_deform, s, v, st);
+    }
     s->launches++;
 }
 static void enqueue_force(MisSim* s, const View& v, int mode, cudaStream_t st) {
-    if (s->G == 8) launch_force<8>(s, v, mode, st); else if (s->G == 16) launch_force<16>(s, v, mode, st); else launch_force<32>(s, v, mode, st);
+    if (s->p.symmetric_pair) {        // sim_taichi.py pair force, fixed 8 lanes per cluster
+        if (s->C == 1) launch_force_sym<1>(s, v, mode, st); else if (s->C == 2) launch_force_sym<2>(s, v, mode, st); else launch_force_sym<4>(s, v, mode, st);
+    } else {
+        MIS_DISPATCH_CG(launch_force, s, v, mode, st);
+    }
     s->launches++;
 }
 

@@ -12,9 +12,9 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
-LIB_PATH = os.path.join(_PKG, "libmis_b200.so")
+LIB_PATH = os.environ.get("MIS_LIB") or os.path.join(_PKG, "libmis_b200.so")   # MIS_LIB: tuning builds only
 SOURCES = ["mis_api.cu"]
-HEADERS = ["mis_math.cuh", "mis_sort.cuh", "mis_neighbors.cuh", "mis_step.cuh", "mis_sdf.cuh"]
+HEADERS = ["mis_math.cuh", "mis_sort.cuh", "mis_neighbors.cuh", "mis_cluster.cuh", "mis_sdf.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -29,7 +29,7 @@ class MisParams(C.Structure):
         ("symmetric_pair", C.c_int), ("identity_rot", C.c_int), ("self_density", C.c_int),
         ("euler", C.c_int), ("no_contact", C.c_int),
         ("lanes_per_particle", C.c_int), ("keep_fields", C.c_int), ("graph_steps", C.c_int),
-        ("two_pass_deform", C.c_int),
+        ("two_pass_deform", C.c_int), ("cluster_size", C.c_int),
     ]
 
 
@@ -37,6 +37,7 @@ class MisNeighborInfo(C.Structure):
     _fields_ = [
         ("total_pairs", C.c_longlong), ("max_neighbors", C.c_int), ("n", C.c_int),
         ("cell_min", C.c_int * 3), ("cell_dim", C.c_int * 3), ("cell_width", C.c_float),
+        ("cluster_size", C.c_int), ("union_entries", C.c_longlong),
     ]
 
 

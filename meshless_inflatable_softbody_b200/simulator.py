@@ -29,7 +29,7 @@ def hash_grid_dims(x0: np.ndarray, h: float):
 class Simulator:
     def __init__(self, x0, config: Optional[SceneConfig] = None, device: str = "cuda:0",
                  lanes_per_particle: int = 0, keep_fields: bool = False, graph_steps: int = 0,
-                 two_pass_deform: bool = False,
+                 two_pass_deform: bool = False, cluster_size: int = 0,
                  apply_defaults: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("meshless_inflatable_softbody_b200.Simulator needs a CUDA device (sm_100a); "
@@ -51,6 +51,7 @@ class Simulator:
         p.self_density, p.euler, p.no_contact = int(c.self_density), int(c.euler), int(not c.ground_contact)
         p.lanes_per_particle, p.keep_fields, p.graph_steps = int(lanes_per_particle), int(keep_fields), int(graph_steps)
         p.two_pass_deform = int(two_pass_deform)
+        p.cluster_size = int(cluster_size)
         self.params = p
         self.hash_grid = (gx, gy, gz)
         with torch.cuda.device(self.device):

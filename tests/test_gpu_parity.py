@@ -85,10 +85,10 @@ def test_rebuild_is_idempotent(sphere3k):
 
 
 # ------------------------------------------------------------------ per-particle fields
-@pytest.mark.parametrize("G", [8, 16, 32])
-def test_fields_match_oracle(sphere3k, G):
+@pytest.mark.parametrize("C,G", [(1, 8), (2, 8), (2, 16), (2, 32), (4, 8), (4, 16), (4, 32), (1, 32)])
+def test_fields_match_oracle(sphere3k, C, G):
     x0 = sphere3k
-    sim, o = _sim(x0, lanes_per_particle=G, keep_fields=True), make_oracle(x0)
+    sim, o = _sim(x0, cluster_size=C, lanes_per_particle=G, keep_fields=True), make_oracle(x0)
     f = sim.fields(want=("rho", "vol"))
     rho, vol = o.volume()
     assert np.abs(_np(f["rho"]) - rho).max() < 3e-6 * rho.max()

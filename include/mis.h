@@ -144,6 +144,44 @@ long long mis_launch_count(MisSim* sim);
  * Advances the state like mis_step.  Synchronises the host.                          */
 int mis_profile_step(MisSim* sim, int n_steps, void* stream, double* ms_deform, double* ms_force);
 
+/* ------------------------------------------------------------------------------------------
+ * DeepSDF MLP (deepsdf.py:9-41, class DeepSDFWithCode; evaluated at sim.py:100).
+ * n_layers Linear layers with dims[0] = 3, dims[1..n_layers-1] = H (network_size, a multiple of
+ * 256), dims[n_layers] = 1; ReLU between layers; every Linear weight-normalised.  The arrays are
+ * the tensors of the reference state dict, per Linear layer l (Sequential index 3 l):
+ *   g_dev[l]    = network.{3l}.parametrizations.weight.original0   [out, 1]
+ *   v_dev[l]    = network.{3l}.parametrizations.weight.original1   [out, in]   (W = g v / |v| per row)
+ *   bias_dev[l] = network.{3l}.bias                                [out]
+ * g_dev / v_dev / bias_dev are HOST arrays of n_layers DEVICE pointers.  Weights are copied
+ * (packed into tensor-core tiles); the caller keeps ownership.  Synchronises the host.        */
+typedef struct MisSdf MisSdf;
+int mis_sdf_create(int n_layers, const int* dims, const float* const* g_dev, const float* const* v_dev,
+                   const float* const* bias_dev, void* stream, MisSdf** out);
+int mis_sdf_destroy(MisSdf* sdf);
+/* sdf(points): DeepSDFWithCode.forward (deepsdf.py:40-41).  points_dev is n*3 fp32; if xform_host
+ * is non-NULL it holds 12 floats (A row-major 3x3, then t) and the network sees A (p - t), the
+ * inverse of the asset placement p_world = p_model @ R + lift (sim.py:46-52); NULL = model-space
+ * input.  sdf_dev[n] receives the values.  grad_dev (n*3, may be NULL) receives d sdf / d p in the
+ * frame of `points` by forward differences of step fd_eps in model space (3 extra evaluations). */
+int mis_sdf_query(MisSdf* sdf, const float* points_dev, int n, const float* xform_host,
+                  float* sdf_dev, float* grad_dev, float fd_eps, void* stream);
+/* kernels launched so far by this network / of which tcgen05 GEMM launches                    */
+long long mis_sdf_launch_count(MisSdf* sdf, long long* gemm_launches);
+/* Measurement aid: device milliseconds of `reps` back-to-back hidden-layer GEMMs (layer 1) on
+ * m rows of scratch activations (CUDA events on `stream`).  Synchronises the host.            */
+int mis_sdf_profile_gemm(MisSdf* sdf, int m, int reps, void* stream, double* ms_total);
+
+/* Per-step obstacle contact (EXTENSION: the reference evaluates DeepSDF once at start-up,
+ * sim.py:100, and its per-step contact is the ground plane, sim.py:238-244).  Generalises
+ * compute_collision_penalty: delta = range - sdf(p_model), f = delta^2 * k_col * n,
+ * n = grad sdf / |grad sdf| in world space, added next to the ground penalty in part_1 / part_2.
+ * xform_host as in mis_sdf_query; bbox_host = model-space min xyz, max xyz of the region where
+ * sdf may be < range (broad phase: particles outside are skipped).  sdf = NULL disables.       */
+int mis_set_sdf_contact(MisSim* sim, MisSdf* sdf, const float* xform_host, const float* bbox_host,
+                        float fd_eps, void* stream);
+/* number of particles that passed the broad phase in the most recent step (synchronises)      */
+int mis_get_contact_count(MisSim* sim, void* stream, int* count);
+
 #ifdef __cplusplus
 }
 #endif

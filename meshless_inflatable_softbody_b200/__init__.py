@@ -10,7 +10,7 @@ import importlib
 from .config import SceneConfig  # noqa: F401
 from . import scenes  # noqa: F401
 
-__all__ = ["SceneConfig", "scenes", "Simulator", "native"]
+__all__ = ["SceneConfig", "scenes", "Simulator", "DeepSDF", "native"]
 
 
 def __getattr__(name):
@@ -18,4 +18,6 @@ def __getattr__(name):
         return importlib.import_module(".native", __name__)
     if name == "Simulator":
         return importlib.import_module(".simulator", __name__).Simulator
+    if name == "DeepSDF":
+        return importlib.import_module(".deepsdf", __name__).DeepSDF
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -5,7 +5,7 @@
 #include "mis_neighbors.cuh"
 #include "mis_sort.cuh"
 #include "mis_cluster.cuh"
-#include "mis_sdf.cuh"
+#include "mis_sdf_host.cuh"
 
 #include <math.h>
 #include <stdio.h>
@@ -75,9 +75,17 @@ struct MisSim {
     // CUDA graph cache for step chunks
     cudaGraphExec_t graph_exec = nullptr;
     int graph_steps = 0, graph_cur = -1;
+    long long graph_launches = 0;
     cudaStream_t graph_stream = nullptr;
-    // DeepSDF contact (extension)
-    SdfState sdf;
+    // DeepSDF obstacle contact (extension)
+    MisSdf* sdf = nullptr;
+    SdfXform sdf_xf{};
+    float3 sdf_lo{}, sdf_hi{};
+    float sdf_eps = 1e-3f;
+    int* con_idx = nullptr;
+    int* con_count = nullptr;
+    float* con_pts = nullptr;
+    float4* fcon = nullptr;
 };
 
 template <typename T>
@@ -124,6 +132,7 @@ static View make_view(MisSim* s) {
     v.vel = s->vel; v.f1 = s->f1; v.fel = s->fel; v.fext = s->fext; v.freem = s->freem; v.matl = s->matl;
     v.RS = s->RS; v.Fd = s->Fd; v.Ks = s->Ks; v.Apq = s->p.keep_fields ? s->Apq : nullptr;
     v.cl_start = s->cl_start; v.cl = s->cl;
+    v.fcon = s->sdf ? s->fcon : nullptr;
     return v;
 }
 
@@ -197,8 +206,7 @@ extern "C" int mis_create(int n, const float* x0_dev, const MisParams* params, v
 extern "C" int mis_destroy(MisSim* s) {
     if (!s) return MIS_OK;
     drop_graph(s);
-    sdf_free(s->sdf);
-    void* ptrs[] = {s->x0_orig, s->coords, s->cell_index, s->keys, s->subkey, s->Ks, s->perm, s->inv_perm, s->rs.keys_alt, s->rs.vals_alt,
+    void* ptrs[] = {s->con_idx, s->con_count, s->con_pts, s->fcon, s->x0_orig, s->coords, s->cell_index, s->keys, s->subkey, s->Ks, s->perm, s->inv_perm, s->rs.keys_alt, s->rs.vals_alt,
                     s->rs.hist, s->rs.hist_scanned, s->rs.tile_tmp, s->bounds_dev, s->max_k_dev, s->cell_start, s->cell_end,
                     s->cell_lin_sorted, s->nbr_count, s->nbr_start, s->scan_tmp, s->nbr, s->cl_count, s->cl_start, s->cl, s->x0m, s->xv[0], s->xv[1], s->vel,
                     s->f1, s->fel, s->fext, s->freem, s->matl, s->RS, s->Fd, s->Apq, s->scratch4, s->stage};
@@ -464,12 +472,31 @@ static void enqueue_force(MisSim* s, const View& v, int mode, cudaStream_t st) {
     s->launches++;
 }
 
+// obstacle contact at the now-current positions: broad phase, MLP chain (value + 3 forward differences), penalty
+static void enqueue_contact(MisSim* s, const View& v, cudaStream_t st) {
+    if (!s->sdf) return;
+    const int n = s->n;
+    cudaMemsetAsync(s->con_count, 0, sizeof(int), st);
+    cudaMemsetAsync(s->fcon, 0, (size_t)n * sizeof(float4), st);
+    k_contact_select<<<nblk(n, 256), 256, 0, st>>>(v.xcur, n, s->sdf_xf, s->sdf_lo, s->sdf_hi, s->con_idx, s->con_count, s->con_pts);
+    s->launches++;
+    const float e = s->sdf_eps;
+    const float3 shifts[4] = {make_float3(0.f, 0.f, 0.f), make_float3(e, 0.f, 0.f), make_float3(0.f, e, 0.f), make_float3(0.f, 0.f, e)};
+    const long long l0 = s->sdf->launches;
+    for (int q = 0; q < 4; q++)
+        sdf_forward(s->sdf, s->con_pts, nullptr, n, s->con_count, s->sdf_xf, shifts[q], s->sdf->vals + (size_t)q * s->sdf->cap, st);
+    s->launches += s->sdf->launches - l0;
+    k_contact_apply<<<nblk(n, 256), 256, 0, st>>>(s->sdf->vals, s->sdf->cap, s->con_idx, s->con_count, 1.f / e, s->sdf_xf, s->p.col_range, s->p.k_col, s->fcon);
+    s->launches++;
+}
+
 // frame-0 style priming at the current x: elastic force, force_1 and the next position
 static int prime(MisSim* s, cudaStream_t st) {
     if (!s->mass_set || !s->material_set) return fail(MIS_E_STATE, "set_mass and set_material must precede startup/step");
     if (!s->p.euler) {
         View v = make_view(s);
         enqueue_deform(s, v, st);
+        enqueue_contact(s, v, st);
         enqueue_force(s, v, MODE_PRIME, st);
         CK_LAUNCH();
     }
@@ -502,12 +529,14 @@ static void enqueue_one_step(MisSim* s, cudaStream_t st) {
         // sim_taichi.py:174-182: forces at frame f, then advance to f+1
         View v = make_view(s);
         enqueue_deform(s, v, st);
+        enqueue_contact(s, v, st);
         enqueue_force(s, v, MODE_EULER, st);
         s->cur ^= 1;
     } else {
         s->cur ^= 1;                       // part_1 of this step was fused into the previous force kernel
         View v = make_view(s);
         enqueue_deform(s, v, st);
+        enqueue_contact(s, v, st);
         enqueue_force(s, v, MODE_STEP, st);
     }
 }
@@ -532,6 +561,7 @@ extern "C" int mis_step(MisSim* s, int n_steps, void* stream) {
                 for (int k = 0; k < chunk; k++) enqueue_one_step(s, st);
                 cudaError_t e = cudaStreamEndCapture(st, &g);
                 s->cur = cur0;
+                s->graph_launches = s->launches - l0;
                 s->launches = l0;
                 if (e != cudaSuccess) return fail(MIS_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
                 e = cudaGraphInstantiate(&s->graph_exec, g, 0);
@@ -540,7 +570,7 @@ extern "C" int mis_step(MisSim* s, int n_steps, void* stream) {
                 s->graph_steps = chunk; s->graph_cur = s->cur; s->graph_stream = st;
             }
             CK(cudaGraphLaunch(s->graph_exec, st));
-            s->launches += 2ll * chunk;
+            s->launches += s->graph_launches;
             done += chunk;                 // cur unchanged after an even number of steps
         }
     }
@@ -641,5 +671,134 @@ extern "C" int mis_profile_step(MisSim* s, int n_steps, void* stream, double* ms
     if (ms_deform) *ms_deform = a;
     if (ms_force) *ms_force = b;
     CK_LAUNCH();
+    return MIS_OK;
+}
+
+// ------------------------------------------------------------------ DeepSDF (deepsdf.py:9-41)
+extern "C" int mis_sdf_create(int n_layers, const int* dims, const float* const* g_dev, const float* const* v_dev,
+                              const float* const* bias_dev, void* stream, MisSdf** out) {
+    if (!out || !dims || !g_dev || !v_dev || !bias_dev || n_layers < 3) return fail(MIS_E_INVALID, "mis_sdf_create: bad argument");
+    const int H = dims[1];
+    if (dims[0] != 3 || dims[n_layers] != 1) return fail(MIS_E_UNSUPPORTED, "mis_sdf_create: network must map 3 -> 1 (deepsdf.py:13,37)");
+    for (int l = 1; l < n_layers; l++) if (dims[l] != H) return fail(MIS_E_UNSUPPORTED, "mis_sdf_create: hidden widths must be equal");
+    if (H % SDF_BN != 0) return fail(MIS_E_UNSUPPORTED, "mis_sdf_create: hidden width must be a multiple of 256");
+    cudaStream_t st = (cudaStream_t)stream;
+    MisSdf* s = new MisSdf();
+    s->L = n_layers; s->H = H;
+#define SALLOC(ptr, cnt) do { cudaError_t e_ = cudaMalloc((void**)&(ptr), (size_t)(cnt) * sizeof(float)); if (e_ != cudaSuccess) { int r_ = fail(MIS_E_CUDA, std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(e_)); sdf_free(s); return r_; } } while (0)
+    SALLOC(s->W0, (size_t)H * 3); SALLOC(s->b0, H); SALLOC(s->wl, H); SALLOC(s->bl, 1);
+    k_sdf_pack_weights<<<H, 256, 0, st>>>(g_dev[0], v_dev[0], H, 3, s->W0, nullptr, nullptr);
+    cudaMemcpyAsync(s->b0, bias_dev[0], H * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    for (int l = 1; l < n_layers - 1; l++) {
+        float *hi = nullptr, *lo = nullptr, *b = nullptr;
+        SALLOC(hi, (size_t)H * H); s->Whi.push_back(hi);
+        SALLOC(lo, (size_t)H * H); s->Wlo.push_back(lo);
+        SALLOC(b, H); s->bh.push_back(b);
+        k_sdf_pack_weights<<<H, 256, 0, st>>>(g_dev[l], v_dev[l], H, H, nullptr, hi, lo);
+        cudaMemcpyAsync(b, bias_dev[l], H * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    }
+    k_sdf_pack_weights<<<1, 256, 0, st>>>(g_dev[n_layers - 1], v_dev[n_layers - 1], 1, H, s->wl, nullptr, nullptr);
+    cudaMemcpyAsync(s->bl, bias_dev[n_layers - 1], sizeof(float), cudaMemcpyDeviceToDevice, st);
+#undef SALLOC
+    s->launches += n_layers;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { int r = fail(MIS_E_CUDA, std::string("mis_sdf_create: ") + cudaGetErrorString(e)); sdf_free(s); return r; }
+    *out = s;
+    return MIS_OK;
+}
+
+extern "C" int mis_sdf_destroy(MisSdf* s) { sdf_free(s); return MIS_OK; }
+
+static SdfXform make_xform(const float* xform_host) {
+    SdfXform xf;
+    for (int k = 0; k < 9; k++) xf.A[k] = xform_host ? xform_host[k] : ((k % 4 == 0) ? 1.f : 0.f);
+    for (int k = 0; k < 3; k++) xf.t[k] = xform_host ? xform_host[9 + k] : 0.f;
+    return xf;
+}
+
+extern "C" int mis_sdf_query(MisSdf* s, const float* points_dev, int n, const float* xform_host,
+                             float* sdf_dev, float* grad_dev, float fd_eps, void* stream) {
+    if (!s || !points_dev || n < 0 || (!sdf_dev && !grad_dev)) return fail(MIS_E_INVALID, "mis_sdf_query: bad argument");
+    if (grad_dev && !(fd_eps > 0.f)) return fail(MIS_E_INVALID, "mis_sdf_query: fd_eps must be positive when a gradient is requested");
+    if (n == 0) return MIS_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const SdfXform xf = make_xform(xform_host);
+    const int chunk = 1 << 16;                     // rows per pass: 4 activation planes of chunk x H floats stay resident
+    CK(sdf_reserve(s, n < chunk ? n : chunk));
+    for (int r0 = 0; r0 < n; r0 += chunk) {
+        const int rows = n - r0 < chunk ? n - r0 : chunk;
+        const float* pts = points_dev + 3 * (size_t)r0;
+        if (!grad_dev) {
+            CK(sdf_forward(s, pts, nullptr, rows, nullptr, xf, make_float3(0.f, 0.f, 0.f), sdf_dev + r0, st));
+        } else {
+            const float3 shifts[4] = {make_float3(0.f, 0.f, 0.f), make_float3(fd_eps, 0.f, 0.f), make_float3(0.f, fd_eps, 0.f), make_float3(0.f, 0.f, fd_eps)};
+            for (int q = 0; q < 4; q++) CK(sdf_forward(s, pts, nullptr, rows, nullptr, xf, shifts[q], s->vals + (size_t)q * s->cap, st));
+            k_sdf_fd_grad<<<nblk(rows, 256), 256, 0, st>>>(s->vals, s->cap, rows, 1.f / fd_eps, xf, sdf_dev ? sdf_dev + r0 : nullptr, grad_dev + 3 * (size_t)r0);
+            s->launches++;
+        }
+    }
+    CK_LAUNCH();
+    return MIS_OK;
+}
+
+extern "C" long long mis_sdf_launch_count(MisSdf* s, long long* gemm_launches) {
+    if (!s) return 0;
+    if (gemm_launches) *gemm_launches = s->gemm_launches;
+    return s->launches;
+}
+
+extern "C" int mis_sdf_profile_gemm(MisSdf* s, int m, int reps, void* stream, double* ms_total) {
+    if (!s || m <= 0 || reps <= 0 || !ms_total) return fail(MIS_E_INVALID, "mis_sdf_profile_gemm: bad argument");
+    if (s->Whi.empty()) return fail(MIS_E_STATE, "network has no hidden layer");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(sdf_reserve(s, m));
+    CK(cudaFuncSetAttribute(k_sdf_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));
+    const int m_pad = (m + 127) / 128 * 128;
+    CK(cudaMemsetAsync(s->act[0][0], 0, (size_t)m_pad * s->H * sizeof(float), st));
+    CK(cudaMemsetAsync(s->act[0][1], 0, (size_t)m_pad * s->H * sizeof(float), st));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    dim3 grid(s->H / SDF_BN, m_pad / SDF_BM);
+    k_sdf_gemm<<<grid, SDF_THREADS, SDF_SMEM_BYTES, st>>>(s->act[0][0], s->act[0][1], s->Whi[0], s->Wlo[0], s->bh[0], s->H, s->H, s->act[1][0], s->act[1][1], nullptr);
+    CK(cudaEventRecord(e0, st));
+    for (int r = 0; r < reps; r++)
+        k_sdf_gemm<<<grid, SDF_THREADS, SDF_SMEM_BYTES, st>>>(s->act[0][0], s->act[0][1], s->Whi[0], s->Wlo[0], s->bh[0], s->H, s->H, s->act[1][0], s->act[1][1], nullptr);
+    CK(cudaEventRecord(e1, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    s->launches += reps + 1; s->gemm_launches += reps + 1;
+    *ms_total = ms;
+    CK_LAUNCH();
+    return MIS_OK;
+}
+
+extern "C" int mis_set_sdf_contact(MisSim* s, MisSdf* sdf, const float* xform_host, const float* bbox_host, float fd_eps, void* stream) {
+    if (!s) return fail(MIS_E_INVALID, "null sim");
+    drop_graph(s);
+    s->dirty = true;
+    if (!sdf) { s->sdf = nullptr; return MIS_OK; }
+    if (!bbox_host || !(fd_eps > 0.f)) return fail(MIS_E_INVALID, "mis_set_sdf_contact: bbox and a positive fd_eps are required");
+    const size_t N = (size_t)s->n;
+    if (!s->fcon) {
+        CK(dalloc(&s->con_idx, N)); CK(dalloc(&s->con_count, (size_t)4)); CK(dalloc(&s->con_pts, 3 * N)); CK(dalloc(&s->fcon, N));
+    }
+    CK(cudaMemsetAsync(s->con_count, 0, 4 * sizeof(int), (cudaStream_t)stream));
+    CK(sdf_reserve(sdf, s->n));
+    CK(cudaFuncSetAttribute(k_sdf_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));
+    s->sdf = sdf; s->sdf_xf = make_xform(xform_host); s->sdf_eps = fd_eps;
+    s->sdf_lo = make_float3(bbox_host[0], bbox_host[1], bbox_host[2]);
+    s->sdf_hi = make_float3(bbox_host[3], bbox_host[4], bbox_host[5]);
+    return MIS_OK;
+}
+
+extern "C" int mis_get_contact_count(MisSim* s, void* stream, int* count) {
+    if (!s || !count) return fail(MIS_E_INVALID, "null argument");
+    *count = 0;
+    if (!s->sdf) return MIS_OK;
+    CK(cudaMemcpyAsync(count, s->con_count, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
     return MIS_OK;
 }

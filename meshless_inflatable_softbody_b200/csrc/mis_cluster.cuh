@@ -51,6 +51,7 @@ struct View {
     float* Apq;                       // optional (keep_fields), 9 floats per slot
     const unsigned long long* cl_start;   // union list offsets per cluster
     const uint32_t* cl;                   // union lists (slot ids)
+    const float4* fcon;                   // optional obstacle-contact force at the current positions (DeepSDF extension)
 };
 
 enum ForceMode { MODE_PRIME = 0, MODE_STEP = 1, MODE_EULER = 2, MODE_EVAL = 3 };
@@ -383,13 +384,14 @@ __global__ void __launch_bounds__(STEP_THREADS, MIS_STEP_MIN_BLOCKS) k_deform_c(
 }
 
 // ---------------------------------------------------------------- integrate (literal order, no FMA)
-__device__ __forceinline__ float3 total_force(float3 fext, float3 fel, float3 v, float y, const Consts& c) {
+__device__ __forceinline__ float3 total_force(float3 fext, float3 fel, float3 v, float y, const Consts& c, float3 fcon) {
     // ((external + elastic) - damping * v) + penalty(x)      sim.py:250,256-257
+    // penalty = ground plane (sim.py:238-244) + optional obstacle contact (zero without a DeepSDF obstacle)
     float pen = ground_penalty_y(y, c);
     float3 f;
-    f.x = __fadd_rn(__fsub_rn(__fadd_rn(fext.x, fel.x), __fmul_rn(c.damping, v.x)), 0.f);
-    f.y = __fadd_rn(__fsub_rn(__fadd_rn(fext.y, fel.y), __fmul_rn(c.damping, v.y)), pen);
-    f.z = __fadd_rn(__fsub_rn(__fadd_rn(fext.z, fel.z), __fmul_rn(c.damping, v.z)), 0.f);
+    f.x = __fadd_rn(__fsub_rn(__fadd_rn(fext.x, fel.x), __fmul_rn(c.damping, v.x)), fcon.x);
+    f.y = __fadd_rn(__fsub_rn(__fadd_rn(fext.y, fel.y), __fmul_rn(c.damping, v.y)), __fadd_rn(pen, fcon.y));
+    f.z = __fadd_rn(__fsub_rn(__fadd_rn(fext.z, fel.z), __fmul_rn(c.damping, v.z)), fcon.z);
     return f;
 }
 // x + cw_mul(dt * v + 0.5 * dt * dt * force / m, free)        sim.py:251
@@ -409,12 +411,13 @@ __device__ __forceinline__ void integrate_epilogue(const View& s, const Consts& 
     const float3 fr = xyz(s.freem[i]);
     float3 v = xyz(s.vel[i]);
     float3 x = xyz(pxi);
+    const float3 fcon = s.fcon ? xyz(s.fcon[i]) : make_float3(0.f, 0.f, 0.f);
     if (mode == MODE_EULER) {
         // sim_taichi.py:161-172: force = ext + el + (-damping v); v' = v + dt f / m * free; x' = x + dt v' * free
         float3 f;
-        f.x = __fadd_rn(__fadd_rn(fext.x, fel.x), __fmul_rn(-c.damping, v.x));
-        f.y = __fadd_rn(__fadd_rn(fext.y, fel.y), __fmul_rn(-c.damping, v.y));
-        f.z = __fadd_rn(__fadd_rn(fext.z, fel.z), __fmul_rn(-c.damping, v.z));
+        f.x = __fadd_rn(__fadd_rn(__fadd_rn(fext.x, fel.x), __fmul_rn(-c.damping, v.x)), fcon.x);
+        f.y = __fadd_rn(__fadd_rn(__fadd_rn(fext.y, fel.y), __fmul_rn(-c.damping, v.y)), fcon.y);
+        f.z = __fadd_rn(__fadd_rn(__fadd_rn(fext.z, fel.z), __fmul_rn(-c.damping, v.z)), fcon.z);
         float3 vn, xn;
         vn.x = __fadd_rn(v.x, __fmul_rn(__fdiv_rn(__fmul_rn(c.dt, f.x), m), fr.x));
         vn.y = __fadd_rn(v.y, __fmul_rn(__fdiv_rn(__fmul_rn(c.dt, f.y), m), fr.y));
@@ -430,14 +433,14 @@ __device__ __forceinline__ void integrate_epilogue(const View& s, const Consts& 
     if (mode == MODE_STEP) {
         // part_2 of this step: force_1 was stored by the previous part_1 (same inputs, same value)
         const float3 F1 = xyz(s.f1[i]);
-        const float3 F2 = total_force(fext, fel, v, x.y, c);
+        const float3 F2 = total_force(fext, fel, v, x.y, c, fcon);
         v.x = part2_axis(v.x, F1.x, F2.x, m, fr.x, c);
         v.y = part2_axis(v.y, F1.y, F2.y, m, fr.y, c);
         v.z = part2_axis(v.z, F1.z, F2.z, m, fr.z, c);
         s.vel[i] = make_float4(v.x, v.y, v.z, 0.f);
     }
     // part_1 of the next step from (x, v, fel) of the now-current frame
-    const float3 F1n = total_force(fext, fel, v, x.y, c);
+    const float3 F1n = total_force(fext, fel, v, x.y, c, fcon);
     float3 xn;
     xn.x = part1_axis(x.x, v.x, F1n.x, m, fr.x, c);
     xn.y = part1_axis(x.y, v.y, F1n.y, m, fr.y, c);

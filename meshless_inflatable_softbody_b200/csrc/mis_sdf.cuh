@@ -1,7 +1,310 @@
-// mis_sdf.cuh -- DeepSDF contact query (extension; deepsdf.py:9-41).  Placeholder state
-// until the GEMM chain lands; see DESIGN.md.
+// mis_sdf.cuh -- DeepSDF MLP (deepsdf.py:9-41, DeepSDFWithCode) as a tcgen05 tensor-core GEMM chain.
+//
+// The network is Linear(3,H)+ReLU, (L-2) x [Linear(H,H)+ReLU], Linear(H,1) with weight_norm on every
+// Linear (W = g * v / ||v|| per output row, deepsdf.py:3,13-37) and Dropout(0.0) = identity.  The
+// reference evaluates it in fp32 (cuBLAS SGEMM, sim.py:100); contact and the design field need
+// fp32-class accuracy, so the hidden layers run as 3xTF32 on the 5th-generation tensor cores:
+//     x = x_hi + x_lo,  x_hi = x with the low 13 mantissa bits cleared (exactly a TF32 number),
+//     X W^T ~= X_hi W_hi^T + X_hi W_lo^T + X_lo W_hi^T        (error ~2^-21 relative, fp32 accumulate in TMEM)
+//
+// Data layout in HBM ("UMMA tiles"): every GEMM operand is stored as the exact shared-memory image the
+// MMA reads, so a tile moves with ONE 1-D TMA bulk copy (cp.async.bulk) and needs no tensor map:
+//   tile (rb, kb) = rows [128 rb, 128 rb+128) x k [32 kb, 32 kb+32) of fp32 = 16 KB at ((rb*KB + kb) * 4096) floats
+//   inside a tile: off(r, k) = (r/8)*256 + (k/4)*32 + (r%8)*4 + (k%4) floats
+//   = the canonical K-major no-swizzle UMMA layout: 8x16-byte core matrices, LBO (K step) 128 B, SBO (8-row step) 1024 B.
+// Activations are produced in this layout (hi and lo planes) by the previous layer's epilogue.
+//
+// Kernel k_sdf_gemm (one 128 x 256 output tile per CTA, 192 threads):
+//   warp 0   : TMA producer  -- per 32-wide k-block: A_hi, A_lo (16 KB each), B_hi, B_lo (2 x 16 KB each) into a 2-stage ring
+//   warp 1   : TMEM allocation + MMA issuer -- 4 k-steps x 3 tcgen05.mma.kind::tf32 (128x256x8) per k-block, fp32 accumulators
+//              in 256 TMEM columns; tcgen05.commit releases the smem stage / signals the epilogue
+//   warps 2-5: epilogue -- tcgen05.ld 32x32b, + bias, ReLU, hi/lo split, 16-byte stores straight into the next layer's tiles
 #pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
 namespace mis {
-struct SdfState {};
-inline void sdf_free(SdfState&) {}
+
+constexpr int SDF_BM = 128, SDF_BN = 256, SDF_BK = 32;
+constexpr int SDF_TILE_FLOATS = 128 * 32;                    // one 128 x 32 fp32 tile
+constexpr int SDF_TILE_BYTES = SDF_TILE_FLOATS * 4;          // 16 KB
+constexpr int SDF_STAGES = 2;
+constexpr int SDF_STAGE_BYTES = 6 * SDF_TILE_BYTES;          // A_hi, A_lo, B_hi[2], B_lo[2]
+constexpr int SDF_SMEM_BYTES = SDF_STAGES * SDF_STAGE_BYTES + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int SDF_THREADS = 192;
+
+__host__ __device__ __forceinline__ size_t sdf_tile_off(int r, int k, int KB) {
+    // float offset of element (r, k) in a tiled matrix with KB k-blocks per row-block
+    return ((size_t)(r >> 7) * KB + (k >> 5)) * SDF_TILE_FLOATS + ((r & 127) >> 3) * 256 + ((k & 31) >> 2) * 32 + (r & 7) * 4 + (k & 3);
+}
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// K-major, no swizzle: LBO = 128 B between core matrices along K, SBO = 1024 B between 8-row groups, descriptor version 1
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256
+constexpr uint32_t SDF_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SDF_BN >> 3) << 17) | ((uint32_t)(SDF_BM >> 4) << 24);
+
+// ---------------------------------------------------------------- the hidden layer
+// Yhi/Ylo[M_pad, N] = split( relu( (Xhi + Xlo)[M_pad, K] (Whi + Wlo)[N, K]^T + bias ) ), all matrices in UMMA tiles.
+// grid = (N / 256, M_pad / 128): n fastest so the CTAs of one row-block run together and share A in L2.
+__global__ void __launch_bounds__(SDF_THREADS, 1) k_sdf_gemm(const float* __restrict__ Xhi, const float* __restrict__ Xlo,
+                                                             const float* __restrict__ Whi, const float* __restrict__ Wlo,
+                                                             const float* __restrict__ bias, int K, int N,
+                                                             float* __restrict__ Yhi, float* __restrict__ Ylo,
+                                                             const int* __restrict__ m_count /* device-side row count, may be null */) {
+    extern __shared__ uint8_t smem_raw[];
+    const int nb = blockIdx.x, mb = blockIdx.y;
+    if (m_count && mb * SDF_BM >= *m_count) return;          // nothing to do for row-blocks past the live rows
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KB = K / SDF_BK;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bias_s = base + SDF_STAGES * SDF_STAGE_BYTES;
+    const uint32_t bars = bias_s + 1024;
+    // full[s] at bars + 8 s, empty[s] at bars + 16 + 8 s, tmem_full at bars + 32, tmem pointer at bars + 40
+    float* bias_sm = reinterpret_cast<float*>(smem_raw + (bias_s - smem_u32(smem_raw)));
+    volatile uint32_t* tmem_ptr_sm = reinterpret_cast<volatile uint32_t*>(smem_raw + (bars + 40 - smem_u32(smem_raw)));
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SDF_STAGES; s++) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 16 + 8 * s, 1); }
+        mbar_init(bars + 32, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + 40), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int t = threadIdx.x; t < SDF_BN; t += SDF_THREADS) bias_sm[t] = bias[nb * SDF_BN + t];
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = *tmem_ptr_sm;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const float* a_hi = Xhi + (size_t)mb * KB * SDF_TILE_FLOATS;
+            const float* a_lo = Xlo + (size_t)mb * KB * SDF_TILE_FLOATS;
+            const float* b_hi0 = Whi + (size_t)(2 * nb) * KB * SDF_TILE_FLOATS;
+            const float* b_hi1 = Whi + (size_t)(2 * nb + 1) * KB * SDF_TILE_FLOATS;
+            const float* b_lo0 = Wlo + (size_t)(2 * nb) * KB * SDF_TILE_FLOATS;
+            const float* b_lo1 = Wlo + (size_t)(2 * nb + 1) * KB * SDF_TILE_FLOATS;
+            for (int kb = 0; kb < KB; kb++) {
+                const int s = kb % SDF_STAGES;
+                const uint32_t ph = (kb / SDF_STAGES) & 1;
+                mbar_wait(bars + 16 + 8 * s, ph ^ 1);               // slot free (first pass returns at once)
+                const uint32_t full = bars + 8 * s;
+                mbar_expect_tx(full, SDF_STAGE_BYTES);
+                const uint32_t st = base + s * SDF_STAGE_BYTES;
+                const size_t o = (size_t)kb * SDF_TILE_FLOATS;
+                tma_bulk_g2s(st + 0 * SDF_TILE_BYTES, a_hi + o, SDF_TILE_BYTES, full);
+                tma_bulk_g2s(st + 1 * SDF_TILE_BYTES, a_lo + o, SDF_TILE_BYTES, full);
+                tma_bulk_g2s(st + 2 * SDF_TILE_BYTES, b_hi0 + o, SDF_TILE_BYTES, full);
+                tma_bulk_g2s(st + 3 * SDF_TILE_BYTES, b_hi1 + o, SDF_TILE_BYTES, full);
+                tma_bulk_g2s(st + 4 * SDF_TILE_BYTES, b_lo0 + o, SDF_TILE_BYTES, full);
+                tma_bulk_g2s(st + 5 * SDF_TILE_BYTES, b_lo1 + o, SDF_TILE_BYTES, full);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < KB; kb++) {
+                const int s = kb % SDF_STAGES;
+                const uint32_t ph = (kb / SDF_STAGES) & 1;
+                mbar_wait(bars + 8 * s, ph);                         // operands landed
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = base + s * SDF_STAGE_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < SDF_BK / 8; ks++) {
+                    const uint32_t ko = ks * 256;                    // 8 floats along K = 2 core matrices = 256 B
+                    const uint64_t ahi = umma_desc(st + 0 * SDF_TILE_BYTES + ko), alo = umma_desc(st + 1 * SDF_TILE_BYTES + ko);
+                    const uint64_t bhi = umma_desc(st + 2 * SDF_TILE_BYTES + ko), blo = umma_desc(st + 4 * SDF_TILE_BYTES + ko);
+                    umma_tf32(tmem_acc, alo, bhi, SDF_IDESC, (kb | ks) ? 1u : 0u);
+                    umma_tf32(tmem_acc, ahi, blo, SDF_IDESC, 1u);
+                    umma_tf32(tmem_acc, ahi, bhi, SDF_IDESC, 1u);
+                }
+                umma_commit(bars + 16 + 8 * s);                      // frees the smem stage when these MMAs retire
+            }
+            umma_commit(bars + 32);                                   // accumulator complete
+        }
+    } else {
+        // epilogue: warp w may touch TMEM lanes [32 (w % 4), 32 (w % 4) + 32)
+        const int q = warp & 3;
+        mbar_wait(bars + 32, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int rl = 32 * q + lane;                                 // row inside the 128-row block
+        const int KBn = N / SDF_BK;                                   // k-blocks of the NEXT layer's A operand
+        const size_t row_off = (size_t)(rl >> 3) * 256 + (rl & 7) * 4;
+#pragma unroll 1
+        for (int c = 0; c < SDF_BN; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
+            const size_t tile = ((size_t)mb * KBn + (size_t)(nb * SDF_BN + c) / SDF_BK) * SDF_TILE_FLOATS + row_off;
+            float4* dhi = reinterpret_cast<float4*>(Yhi + tile);
+            float4* dlo = reinterpret_cast<float4*>(Ylo + tile);
+#pragma unroll
+            for (int kc = 0; kc < 8; kc++) {
+                float h[4], l[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const float y = fmaxf(__uint_as_float(v[4 * kc + e]) + bias_sm[c + 4 * kc + e], 0.f);
+                    h[e] = tf32_hi(y);
+                    l[e] = y - h[e];
+                }
+                dhi[kc * 8] = make_float4(h[0], h[1], h[2], h[3]);    // next core matrix along K: +32 floats = 8 float4
+                dlo[kc * 8] = make_float4(l[0], l[1], l[2], l[3]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(256u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- weights
+// weight_norm (deepsdf.py:3): W[o, :] = g[o] * v[o, :] / ||v[o, :]||.  One block per output row; writes the
+// plain fp32 row (first / last layer) and/or the hi / lo UMMA tiles (hidden layers).
+__global__ void __launch_bounds__(256) k_sdf_pack_weights(const float* __restrict__ g, const float* __restrict__ v, int n_out, int n_in,
+                                                          float* __restrict__ plain, float* __restrict__ Whi, float* __restrict__ Wlo) {
+    __shared__ float red[8];
+    __shared__ float scale_s;
+    const int o = blockIdx.x;
+    float ss = 0.f;
+    for (int k = threadIdx.x; k < n_in; k += 256) { float x = v[(size_t)o * n_in + k]; ss += x * x; }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; w++) t += red[w];
+        scale_s = g[o] / sqrtf(t);
+    }
+    __syncthreads();
+    const float sc = scale_s;
+    const int KB = n_in / SDF_BK;
+    for (int k = threadIdx.x; k < n_in; k += 256) {
+        const float w = v[(size_t)o * n_in + k] * sc;
+        if (plain) plain[(size_t)o * n_in + k] = w;
+        if (Whi) {
+            const size_t off = sdf_tile_off(o, k, KB);
+            const float h = tf32_hi(w);
+            Whi[off] = h; Wlo[off] = w - h;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- first layer: Linear(3, H) + ReLU on CUDA cores (K = 3)
+// points are taken through p_model = A (p - t) first (A row-major 3x3; identity / zero for model-space input).
+// One thread per (row, 4 consecutive outputs) = one 16-byte chunk of the hi and lo tiles.
+struct SdfXform { float A[9]; float t[3]; };
+
+__global__ void __launch_bounds__(256) k_sdf_layer0(const float* __restrict__ pts, const int* __restrict__ idx, int m, int m_pad,
+                                                    const int* __restrict__ m_count, SdfXform xf, float3 shift,
+                                                    const float* __restrict__ W0 /* [H,3] */, const float* __restrict__ b0, int H,
+                                                    float* __restrict__ Yhi, float* __restrict__ Ylo) {
+    const int chunks = H / 4;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = (int)(gid / chunks), ch = (int)(gid % chunks);
+    if (r >= m_pad) return;
+    const int live = m_count ? min(*m_count, m) : m;
+    if (m_count && (r & ~127) >= live) return;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (r < live) {
+        const int src = idx ? idx[r] : r;
+        const float px = pts[3 * (size_t)src] - xf.t[0], py = pts[3 * (size_t)src + 1] - xf.t[1], pz = pts[3 * (size_t)src + 2] - xf.t[2];
+        x = xf.A[0] * px + xf.A[1] * py + xf.A[2] * pz + shift.x;
+        y = xf.A[3] * px + xf.A[4] * py + xf.A[5] * pz + shift.y;
+        z = xf.A[6] * px + xf.A[7] * py + xf.A[8] * pz + shift.z;
+    }
+    float h[4], l[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const int o = 4 * ch + e;
+        // nn.Linear: x W^T + b, accumulated in k order like a dot product
+        float acc = x * W0[3 * o];
+        acc = fmaf(y, W0[3 * o + 1], acc);
+        acc = fmaf(z, W0[3 * o + 2], acc);
+        acc = fmaxf(acc + b0[o], 0.f);
+        h[e] = tf32_hi(acc); l[e] = acc - h[e];
+    }
+    const size_t off = sdf_tile_off(r, 4 * ch, H / SDF_BK);
+    *reinterpret_cast<float4*>(Yhi + off) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(Ylo + off) = make_float4(l[0], l[1], l[2], l[3]);
+}
+
+// ---------------------------------------------------------------- last layer: Linear(H, 1) on CUDA cores
+// One warp per row; lane = k-block, fixed summation order (deterministic).
+__global__ void __launch_bounds__(256) k_sdf_last(const float* __restrict__ Xhi, const float* __restrict__ Xlo, int m, const int* __restrict__ m_count,
+                                                  const float* __restrict__ w /* [H] */, const float* __restrict__ b, int H, float* __restrict__ out) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int live = m_count ? min(*m_count, m) : m;
+    if (r >= live) return;
+    const int KB = H / SDF_BK;
+    float acc = 0.f;
+    for (int kb = lane; kb < KB; kb += 32) {
+        const size_t base = ((size_t)(r >> 7) * KB + kb) * SDF_TILE_FLOATS + ((r & 127) >> 3) * 256 + (r & 7) * 4;
+#pragma unroll
+        for (int kc = 0; kc < 8; kc++) {
+            const float4 h = *reinterpret_cast<const float4*>(Xhi + base + kc * 32);
+            const float4 l = *reinterpret_cast<const float4*>(Xlo + base + kc * 32);
+            const float4 ww = *reinterpret_cast<const float4*>(w + kb * 32 + kc * 4);
+            acc = fmaf(h.x + l.x, ww.x, acc); acc = fmaf(h.y + l.y, ww.y, acc);
+            acc = fmaf(h.z + l.z, ww.z, acc); acc = fmaf(h.w + l.w, ww.w, acc);
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) out[r] = acc + b[0];
+}
+
 }  // namespace mis

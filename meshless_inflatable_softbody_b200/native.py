@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.environ.get("MIS_LIB") or os.path.join(_PKG, "libmis_b200.so")   # MIS_LIB: tuning builds only
 SOURCES = ["mis_api.cu"]
-HEADERS = ["mis_math.cuh", "mis_sort.cuh", "mis_neighbors.cuh", "mis_cluster.cuh", "mis_sdf.cuh"]
+HEADERS = ["mis_math.cuh", "mis_sort.cuh", "mis_neighbors.cuh", "mis_cluster.cuh", "mis_sdf.cuh", "mis_sdf_host.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -99,6 +99,14 @@ SYMBOLS = {
     "mis_eval_forces": (C.c_int, [_vp, _fp, _fp, _vp]),
     "mis_launch_count": (C.c_longlong, [_vp]),
     "mis_profile_step": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "mis_sdf_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                 C.POINTER(C.c_void_p), _vp, C.POINTER(C.c_void_p)]),
+    "mis_sdf_destroy": (C.c_int, [_vp]),
+    "mis_sdf_query": (C.c_int, [_vp, _fp, C.c_int, C.POINTER(C.c_float), _fp, _fp, C.c_float, _vp]),
+    "mis_sdf_launch_count": (C.c_longlong, [_vp, C.POINTER(C.c_longlong)]),
+    "mis_sdf_profile_gemm": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.POINTER(C.c_double)]),
+    "mis_set_sdf_contact": (C.c_int, [_vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, _vp]),
+    "mis_get_contact_count": (C.c_int, [_vp, _vp, C.POINTER(C.c_int)]),
 }
 
 _lib = None

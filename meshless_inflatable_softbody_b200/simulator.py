@@ -160,6 +160,28 @@ class Simulator:
     def rebuild_neighbors(self):
         native.check(self.L.mis_build_neighbors(self._h, self._st()), "mis_build_neighbors")
 
+    # ------------------------------------------------------------------ obstacle contact (extension)
+    def set_sdf_obstacle(self, sdf, bbox_model, xform=None, fd_eps: float = 1e-3):
+        """Per-step contact against a DeepSDF-encoded obstacle (extension; the reference evaluates its SDF once,
+        sim.py:100, and only the ground plane per step, sim.py:238-244).  Generalises compute_collision_penalty:
+        delta = collision_range - sdf(p_model), f = delta^2 * stiffness * n.  bbox_model = (min xyz, max xyz) of the
+        model-space region where sdf can be below collision_range; xform = deepsdf.world_to_model_xform(...) or None
+        (obstacle given in world coordinates).  sdf=None removes the obstacle."""
+        if sdf is None:
+            native.check(self.L.mis_set_sdf_contact(self._h, None, None, None, 0.0, self._st()), "mis_set_sdf_contact")
+            self._sdf = None
+            return
+        xf = None if xform is None else (C.c_float * 12)(*[float(v) for v in xform])
+        bb = (C.c_float * 6)(*[float(v) for v in np.asarray(bbox_model, np.float32).reshape(-1)])
+        self.stream.wait_stream(sdf.stream)
+        native.check(self.L.mis_set_sdf_contact(self._h, sdf._h, xf, bb, float(fd_eps), self._st()), "mis_set_sdf_contact")
+        self._sdf = sdf          # keep the network alive while the scene uses it
+
+    def contact_count(self) -> int:
+        c = C.c_int(0)
+        native.check(self.L.mis_get_contact_count(self._h, self._st(), C.byref(c)), "mis_get_contact_count")
+        return int(c.value)
+
     # ------------------------------------------------------------------ state export
     def position_velocity(self):
         x = torch.empty((self.n, 3), device=self.device, dtype=torch.float32)

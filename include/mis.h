@@ -128,6 +128,12 @@ int mis_step(MisSim* sim, int n_steps, void* stream);
 /* position[f], velocity[f] of the current frame (sim.py:334,368-369), caller order.  */
 int mis_get_state(MisSim* sim, float* x_dev, float* v_dev, void* stream);
 int mis_get_state_host(MisSim* sim, float* x_host, float* v_host, void* stream);
+/* Halo plumbing for slab-partitioned scenes (no reference counterpart: the reference is single-GPU).
+ * part_1 of the NEXT step is fused into the force kernel, so after mis_step the positions of frame f+1
+ * already exist; these two calls read / overwrite them for a subset of particles (caller ids, int32):
+ * a rank sends the new positions of its boundary particles and overwrites its ghosts' before the next step. */
+int mis_gather_next_positions(MisSim* sim, const int* ids_dev, int count, float* x_dev /* count*3 */, void* stream);
+int mis_scatter_next_positions(MisSim* sim, const int* ids_dev, int count, const float* x_dev /* count*3 */, void* stream);
 /* Per-particle fields of the current frame, caller order; any pointer may be NULL.
  * A_pq (needs keep_fields), R = U V^T, def_grad, S = compute_sigma, elastic force,
  * rho, volume  (sim.py:154-235).                                                    */

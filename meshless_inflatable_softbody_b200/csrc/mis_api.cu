@@ -638,6 +638,26 @@ extern "C" int mis_eval_forces(MisSim* s, const float* x_dev, float* fel_dev, vo
     return MIS_OK;
 }
 
+// positions of frame f+1 (written by the fused part_1): xv[cur ^ 1] once the state is primed
+extern "C" int mis_gather_next_positions(MisSim* s, const int* ids_dev, int count, float* x_dev, void* stream) {
+    if (!s || count < 0 || (count > 0 && (!ids_dev || !x_dev))) return fail(MIS_E_INVALID, "bad argument");
+    if (!s->started || s->dirty) return fail(MIS_E_STATE, "mis_gather_next_positions needs a primed state (mis_startup + mis_step)");
+    if (s->p.euler) return fail(MIS_E_UNSUPPORTED, "halo plumbing supports the velocity-Verlet path only");
+    if (count == 0) return MIS_OK;
+    k_subset_gather<<<nblk(count, 256), 256, 0, (cudaStream_t)stream>>>(s->xv[s->cur ^ 1], s->inv_perm, ids_dev, count, x_dev);
+    CK_LAUNCH(); s->launches++;
+    return MIS_OK;
+}
+extern "C" int mis_scatter_next_positions(MisSim* s, const int* ids_dev, int count, const float* x_dev, void* stream) {
+    if (!s || count < 0 || (count > 0 && (!ids_dev || !x_dev))) return fail(MIS_E_INVALID, "bad argument");
+    if (!s->started || s->dirty) return fail(MIS_E_STATE, "mis_scatter_next_positions needs a primed state (mis_startup + mis_step)");
+    if (s->p.euler) return fail(MIS_E_UNSUPPORTED, "halo plumbing supports the velocity-Verlet path only");
+    if (count == 0) return MIS_OK;
+    k_subset_scatter<<<nblk(count, 256), 256, 0, (cudaStream_t)stream>>>(s->xv[s->cur ^ 1], s->inv_perm, ids_dev, count, x_dev);
+    CK_LAUNCH(); s->launches++;
+    return MIS_OK;
+}
+
 extern "C" long long mis_launch_count(MisSim* s) { return s ? s->launches : 0; }
 
 // n_steps steps launched one kernel at a time with a CUDA event pair around each launch on

@@ -605,6 +605,19 @@ __global__ void __launch_bounds__(256) k_export_vec3(const float4* __restrict__ 
     float4 v = src[inv_perm[i]];
     dst[3 * i] = v.x; dst[3 * i + 1] = v.y; dst[3 * i + 2] = v.z;
 }
+// halo plumbing: subset of particles by caller id <-> packed vec3 buffer
+__global__ void __launch_bounds__(256) k_subset_gather(const float4* __restrict__ src, const int* __restrict__ inv_perm, const int* __restrict__ ids, int count, float* __restrict__ out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const float4 v = src[inv_perm[ids[k]]];
+    out[3 * (size_t)k] = v.x; out[3 * (size_t)k + 1] = v.y; out[3 * (size_t)k + 2] = v.z;
+}
+__global__ void __launch_bounds__(256) k_subset_scatter(float4* __restrict__ dst, const int* __restrict__ inv_perm, const int* __restrict__ ids, int count, const float* __restrict__ in) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    float4* d = dst + inv_perm[ids[k]];
+    d->x = in[3 * (size_t)k]; d->y = in[3 * (size_t)k + 1]; d->z = in[3 * (size_t)k + 2];   // .w (volume) untouched
+}
 // export fields: which = 0 R, 1 S (full symmetric 3x3), 2 F, 3 A, 4 rho, 5 vol
 __global__ void __launch_bounds__(256) k_export_field(View s, const int* __restrict__ inv_perm, int which, float* __restrict__ dst) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -99,6 +99,8 @@ SYMBOLS = {
     "mis_eval_forces": (C.c_int, [_vp, _fp, _fp, _vp]),
     "mis_launch_count": (C.c_longlong, [_vp]),
     "mis_profile_step": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "mis_gather_next_positions": (C.c_int, [_vp, _ip, C.c_int, _fp, _vp]),
+    "mis_scatter_next_positions": (C.c_int, [_vp, _ip, C.c_int, _fp, _vp]),
     "mis_sdf_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_void_p), _vp, C.POINTER(C.c_void_p)]),
     "mis_sdf_destroy": (C.c_int, [_vp]),

@@ -160,6 +160,22 @@ class Simulator:
     def rebuild_neighbors(self):
         native.check(self.L.mis_build_neighbors(self._h, self._st()), "mis_build_neighbors")
 
+    # ------------------------------------------------------------------ halo plumbing (slab.py)
+    def gather_next_positions(self, ids: torch.Tensor) -> torch.Tensor:
+        """New positions x(f+1) (already written by the fused part_1) of the particles `ids` (int32, caller ids)."""
+        out = torch.empty((int(ids.numel()), 3), device=self.device, dtype=torch.float32)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        native.check(self.L.mis_gather_next_positions(self._h, ids.data_ptr(), int(ids.numel()), out.data_ptr(), self._st()),
+                     "mis_gather_next_positions")
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        return out
+
+    def scatter_next_positions(self, ids: torch.Tensor, x: torch.Tensor):
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        native.check(self.L.mis_scatter_next_positions(self._h, ids.data_ptr(), int(ids.numel()), x.data_ptr(), self._st()),
+                     "mis_scatter_next_positions")
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)     # keeps `x` alive until the scatter has read it
+
     # ------------------------------------------------------------------ obstacle contact (extension)
     def set_sdf_obstacle(self, sdf, bbox_model, xform=None, fd_eps: float = 1e-3):
         """Per-step contact against a DeepSDF-encoded obstacle (extension; the reference evaluates its SDF once,

@@ -1,0 +1,82 @@
+"""Slab-partitioned scene on the CUDA engine: all ranks of a 2- and 3-way partition driven from one process on one GPU
+(device-to-device halo copies) against the single-domain run of the same scene; NCCL run when >= 2 GPUs are visible."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import make_oracle
+from meshless_inflatable_softbody_b200 import SceneConfig, scenes
+from meshless_inflatable_softbody_b200.slab import SlabPartition, SlabSimulator, step_in_process
+
+pytestmark = pytest.mark.gpu
+FLOOR_MULT = 4.0
+
+
+def _beam(n=5000):
+    x0 = scenes.jittered_beam(n, seed=0, aspect=(6.0, 1.0, 1.0), centre=(0.0, 0.012, 0.0))
+    x0[:, 1] += 0.0006 - x0[:, 1].min()           # low drop: ground contact within the run
+    return x0.astype(np.float32)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_run_matches_single_domain(world):
+    from meshless_inflatable_softbody_b200 import Simulator
+    cfg = SceneConfig()
+    x0 = _beam()
+    steps = 60
+    part = SlabPartition.build(x0, cfg.h, world)
+    sims = [SlabSimulator(x0, cfg, rank=r, world_size=world, partition=part, in_process=True) for r in range(world)]
+    for s in sims:
+        s.sim.startup(); s.sim.step(0)
+    step_in_process(sims, 0)
+    step_in_process(sims, steps)
+    X = np.zeros((len(x0), 3), np.float32); V = np.zeros_like(X)
+    for s in sims:
+        x, v = s.position_velocity()
+        X[s.plan.owned] = x.cpu().numpy(); V[s.plan.owned] = v.cpu().numpy()
+    one = Simulator(x0, cfg)
+    one.startup(); one.step(steps)
+    x1, v1 = (t.cpu().numpy() for t in one.position_velocity())
+    # tolerance: 4 x the oracle's own fp32 reorder floor on this scene (each domain sorts / sums in its own order)
+    a, b = make_oracle(x0, cfg), make_oracle(x0, cfg)
+    b.set_order(1)
+    a.startup(cfg.initial_velocity); b.startup(cfg.initial_velocity)
+    a.step(steps); b.step(steps)
+    fx, fv = np.abs(a.position() - b.position()).max(), np.abs(a.velocity() - b.velocity()).max()
+    assert np.isfinite(X).all() and np.isfinite(V).all()
+    assert np.abs(X - x1).max() <= FLOOR_MULT * fx + 4e-9, (np.abs(X - x1).max(), fx)
+    assert np.abs(V - v1).max() <= FLOOR_MULT * fv + 2e-5, (np.abs(V - v1).max(), fv)
+    assert np.abs(X - a.position()).max() <= FLOOR_MULT * fx + 4e-9
+    assert V[:, 1].max() > -0.4 - 10.0 * steps * cfg.time_step + 0.01      # some particle is slower than free fall: ground contact acted
+    assert all(s.exchanges == steps + 1 for s in sims)
+
+
+def _nccl_worker(rank, world, x0, steps, port, out_dir):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    sim = SlabSimulator(x0, SceneConfig(), rank=rank, world_size=world, device=f"cuda:{rank}")
+    sim.startup(); sim.step(steps)
+    X, V = sim.gather_global()
+    if rank == 0:
+        np.save(os.path.join(out_dir, "X.npy"), X.cpu().numpy()); np.save(os.path.join(out_dir, "V.npy"), V.cpu().numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_nccl_halo_exchange_two_gpus(tmp_path):
+    import torch.multiprocessing as mp
+    from meshless_inflatable_softbody_b200 import Simulator
+    x0 = _beam(8000)
+    steps = 40
+    mp.spawn(_nccl_worker, args=(2, x0, steps, 29731, str(tmp_path)), nprocs=2, join=True)
+    X, V = np.load(tmp_path / "X.npy"), np.load(tmp_path / "V.npy")
+    one = Simulator(x0, SceneConfig())
+    one.startup(); one.step(steps)
+    x1, v1 = (t.cpu().numpy() for t in one.position_velocity())
+    assert np.abs(X - x1).max() < 2e-7 and np.abs(V - v1).max() < 2e-3

@@ -185,8 +185,11 @@ int mis_sdf_profile_gemm(MisSdf* sdf, int m, int reps, void* stream, double* ms_
  * sdf may be < range (broad phase: particles outside are skipped).  sdf = NULL disables.       */
 int mis_set_sdf_contact(MisSim* sim, MisSdf* sdf, const float* xform_host, const float* bbox_host,
                         float fd_eps, void* stream);
-/* number of particles that passed the broad phase in the most recent step (synchronises)      */
-int mis_get_contact_count(MisSim* sim, void* stream, int* count);
+/* obstacle-contact force at the current frame's positions (n*3, caller order)                  */
+int mis_get_contact_force(MisSim* sim, float* f_dev, void* stream);
+/* most recent step: count[0] = particles that passed the broad phase (MLP evaluated),
+ * count[1] = particles inside the contact band (normal evaluated, force applied).  Synchronises. */
+int mis_get_contact_count(MisSim* sim, void* stream, int count[2]);
 
 #ifdef __cplusplus
 }

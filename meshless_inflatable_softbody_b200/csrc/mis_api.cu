@@ -82,9 +82,9 @@ struct MisSim {
     SdfXform sdf_xf{};
     float3 sdf_lo{}, sdf_hi{};
     float sdf_eps = 1e-3f;
-    int* con_idx = nullptr;
-    int* con_count = nullptr;
-    float* con_pts = nullptr;
+    int *con_idx = nullptr, *con_idx2 = nullptr;
+    int* con_count = nullptr;                 // [0] broad-phase candidates, [1] particles in the contact band
+    float *con_pts = nullptr, *con_pts2 = nullptr, *con_s0 = nullptr;
     float4* fcon = nullptr;
 };
 
@@ -206,7 +206,7 @@ extern "C" int mis_create(int n, const float* x0_dev, const MisParams* params, v
 extern "C" int mis_destroy(MisSim* s) {
     if (!s) return MIS_OK;
     drop_graph(s);
-    void* ptrs[] = {s->con_idx, s->con_count, s->con_pts, s->fcon, s->x0_orig, s->coords, s->cell_index, s->keys, s->subkey, s->Ks, s->perm, s->inv_perm, s->rs.keys_alt, s->rs.vals_alt,
+    void* ptrs[] = {s->con_idx, s->con_idx2, s->con_count, s->con_pts, s->con_pts2, s->con_s0, s->fcon, s->x0_orig, s->coords, s->cell_index, s->keys, s->subkey, s->Ks, s->perm, s->inv_perm, s->rs.keys_alt, s->rs.vals_alt,
                     s->rs.hist, s->rs.hist_scanned, s->rs.tile_tmp, s->bounds_dev, s->max_k_dev, s->cell_start, s->cell_end,
                     s->cell_lin_sorted, s->nbr_count, s->nbr_start, s->scan_tmp, s->nbr, s->cl_count, s->cl_start, s->cl, s->x0m, s->xv[0], s->xv[1], s->vel,
                     s->f1, s->fel, s->fext, s->freem, s->matl, s->RS, s->Fd, s->Apq, s->scratch4, s->stage};
@@ -472,22 +472,27 @@ static void enqueue_force(MisSim* s, const View& v, int mode, cudaStream_t st) {
     s->launches++;
 }
 
-// obstacle contact at the now-current positions: broad phase, MLP chain (value + 3 forward differences), penalty
+// obstacle contact at the now-current positions: broad phase (bounding box) -> MLP values -> narrow phase (contact band)
+// -> three forward-difference evaluations of the particles in contact -> penalty force.  No host synchronisation:
+// the live row counts stay on the device and dead row-blocks of the GEMM grid exit at once.
 static void enqueue_contact(MisSim* s, const View& v, cudaStream_t st) {
     if (!s->sdf) return;
     const int n = s->n;
-    cudaMemsetAsync(s->con_count, 0, sizeof(int), st);
+    MisSdf* net = s->sdf;
+    cudaMemsetAsync(s->con_count, 0, 2 * sizeof(int), st);
     cudaMemsetAsync(s->fcon, 0, (size_t)n * sizeof(float4), st);
     k_contact_select<<<nblk(n, 256), 256, 0, st>>>(v.xcur, n, s->sdf_xf, s->sdf_lo, s->sdf_hi, s->con_idx, s->con_count, s->con_pts);
-    s->launches++;
+    const long long l0 = net->launches;
+    sdf_forward(net, s->con_pts, nullptr, n, s->con_count, s->sdf_xf, make_float3(0.f, 0.f, 0.f), net->vals, st);
+    k_contact_narrow<<<nblk(n, 256), 256, 0, st>>>(net->vals, s->con_idx, s->con_pts, s->con_count, s->p.col_range,
+                                                   s->con_idx2, s->con_pts2, s->con_s0, s->con_count + 1);
     const float e = s->sdf_eps;
-    const float3 shifts[4] = {make_float3(0.f, 0.f, 0.f), make_float3(e, 0.f, 0.f), make_float3(0.f, e, 0.f), make_float3(0.f, 0.f, e)};
-    const long long l0 = s->sdf->launches;
-    for (int q = 0; q < 4; q++)
-        sdf_forward(s->sdf, s->con_pts, nullptr, n, s->con_count, s->sdf_xf, shifts[q], s->sdf->vals + (size_t)q * s->sdf->cap, st);
-    s->launches += s->sdf->launches - l0;
-    k_contact_apply<<<nblk(n, 256), 256, 0, st>>>(s->sdf->vals, s->sdf->cap, s->con_idx, s->con_count, 1.f / e, s->sdf_xf, s->p.col_range, s->p.k_col, s->fcon);
-    s->launches++;
+    const float3 shifts[3] = {make_float3(e, 0.f, 0.f), make_float3(0.f, e, 0.f), make_float3(0.f, 0.f, e)};
+    for (int q = 0; q < 3; q++)
+        sdf_forward(net, s->con_pts2, nullptr, n, s->con_count + 1, s->sdf_xf, shifts[q], net->vals + (size_t)(q + 1) * net->cap, st);
+    k_contact_apply<<<nblk(n, 256), 256, 0, st>>>(s->con_s0, net->vals + net->cap, net->cap, s->con_idx2, s->con_count + 1, 1.f / e, s->sdf_xf,
+                                                  s->p.col_range, s->p.k_col, s->fcon);
+    s->launches += 3 + (net->launches - l0);
 }
 
 // frame-0 style priming at the current x: elastic force, force_1 and the next position
@@ -803,7 +808,8 @@ extern "C" int mis_set_sdf_contact(MisSim* s, MisSdf* sdf, const float* xform_ho
     if (!bbox_host || !(fd_eps > 0.f)) return fail(MIS_E_INVALID, "mis_set_sdf_contact: bbox and a positive fd_eps are required");
     const size_t N = (size_t)s->n;
     if (!s->fcon) {
-        CK(dalloc(&s->con_idx, N)); CK(dalloc(&s->con_count, (size_t)4)); CK(dalloc(&s->con_pts, 3 * N)); CK(dalloc(&s->fcon, N));
+        CK(dalloc(&s->con_idx, N)); CK(dalloc(&s->con_idx2, N)); CK(dalloc(&s->con_count, (size_t)4));
+        CK(dalloc(&s->con_pts, 3 * N)); CK(dalloc(&s->con_pts2, 3 * N)); CK(dalloc(&s->con_s0, N)); CK(dalloc(&s->fcon, N));
     }
     CK(cudaMemsetAsync(s->con_count, 0, 4 * sizeof(int), (cudaStream_t)stream));
     CK(sdf_reserve(sdf, s->n));
@@ -814,11 +820,21 @@ extern "C" int mis_set_sdf_contact(MisSim* s, MisSdf* sdf, const float* xform_ho
     return MIS_OK;
 }
 
+extern "C" int mis_get_contact_force(MisSim* s, float* f_dev, void* stream) {
+    if (!s || !f_dev) return fail(MIS_E_INVALID, "null argument");
+    if (!s->sdf) return fail(MIS_E_STATE, "no obstacle set (mis_set_sdf_contact)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->started && s->dirty) { int rc = prime(s, st); if (rc) return rc; }
+    k_export_vec3<<<nblk(s->n, 256), 256, 0, st>>>(s->fcon, s->inv_perm, s->n, f_dev);
+    CK_LAUNCH(); s->launches++;
+    return MIS_OK;
+}
+
 extern "C" int mis_get_contact_count(MisSim* s, void* stream, int* count) {
     if (!s || !count) return fail(MIS_E_INVALID, "null argument");
-    *count = 0;
+    count[0] = count[1] = 0;
     if (!s->sdf) return MIS_OK;
-    CK(cudaMemcpyAsync(count, s->con_count, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaMemcpyAsync(count, s->con_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
     return MIS_OK;
 }

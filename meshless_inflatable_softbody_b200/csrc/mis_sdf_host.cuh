@@ -116,14 +116,35 @@ __global__ void __launch_bounds__(256) k_contact_select(const float4* __restrict
     }
 }
 
-// contact law: delta = range - sdf(p_model); f = delta^2 k n, n = grad / |grad| in world space
-__global__ void __launch_bounds__(256) k_contact_apply(const float* __restrict__ vals, int cap, const int* __restrict__ idx, const int* __restrict__ count,
-                                                       float inv_eps, SdfXform xf, float range, float k_col, float4* __restrict__ fcon) {
+// narrow phase: keep the candidates whose value is inside the contact band (sdf < range); only they need a normal
+__global__ void __launch_bounds__(256) k_contact_narrow(const float* __restrict__ vals, const int* __restrict__ idx, const float* __restrict__ pts,
+                                                        const int* __restrict__ count, float range,
+                                                        int* __restrict__ idx2, float* __restrict__ pts2, float* __restrict__ s0c, int* __restrict__ count2) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= *count) return;
-    const float s0 = vals[r];
-    if (!(s0 < range)) return;
-    const float gx = (vals[cap + r] - s0) * inv_eps, gy = (vals[2 * (size_t)cap + r] - s0) * inv_eps, gz = (vals[3 * (size_t)cap + r] - s0) * inv_eps;
+    const bool in = r < *count && vals[r] < range;
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    int basep = 0;
+    if (lane == __ffs(m) - 1) basep = atomicAdd(count2, __popc(m));
+    basep = __shfl_sync(0xffffffffu, basep, __ffs(m) - 1);
+    if (in) {
+        const int q = basep + __popc(m & ((1u << lane) - 1));
+        idx2[q] = idx[r];
+        pts2[3 * (size_t)q] = pts[3 * (size_t)r]; pts2[3 * (size_t)q + 1] = pts[3 * (size_t)r + 1]; pts2[3 * (size_t)q + 2] = pts[3 * (size_t)r + 2];
+        s0c[q] = vals[r];
+    }
+}
+
+// contact law: delta = range - sdf(p_model); f = delta^2 k n, n = grad / |grad| in world space.
+// fd holds the three forward-difference evaluations of the in-contact particles (planes of `cap`).
+__global__ void __launch_bounds__(256) k_contact_apply(const float* __restrict__ s0c, const float* __restrict__ fd, int cap, const int* __restrict__ idx2,
+                                                       const int* __restrict__ count2, float inv_eps, SdfXform xf, float range, float k_col,
+                                                       float4* __restrict__ fcon) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= *count2) return;
+    const float s0 = s0c[r];
+    const float gx = (fd[r] - s0) * inv_eps, gy = (fd[(size_t)cap + r] - s0) * inv_eps, gz = (fd[2 * (size_t)cap + r] - s0) * inv_eps;
     float wx = xf.A[0] * gx + xf.A[3] * gy + xf.A[6] * gz;
     float wy = xf.A[1] * gx + xf.A[4] * gy + xf.A[7] * gz;
     float wz = xf.A[2] * gx + xf.A[5] * gy + xf.A[8] * gz;
@@ -131,7 +152,7 @@ __global__ void __launch_bounds__(256) k_contact_apply(const float* __restrict__
     if (!(nn > 1e-20f)) return;
     const float d = range - s0;
     const float f = d * d * k_col / nn;
-    fcon[idx[r]] = make_float4(f * wx, f * wy, f * wz, 0.f);
+    fcon[idx2[r]] = make_float4(f * wx, f * wy, f * wz, 0.f);
 }
 
 }  // namespace mis

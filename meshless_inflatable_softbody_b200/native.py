@@ -108,6 +108,7 @@ SYMBOLS = {
     "mis_sdf_launch_count": (C.c_longlong, [_vp, C.POINTER(C.c_longlong)]),
     "mis_sdf_profile_gemm": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.POINTER(C.c_double)]),
     "mis_set_sdf_contact": (C.c_int, [_vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, _vp]),
+    "mis_get_contact_force": (C.c_int, [_vp, _fp, _vp]),
     "mis_get_contact_count": (C.c_int, [_vp, _vp, C.POINTER(C.c_int)]),
 }
 

@@ -193,10 +193,21 @@ class Simulator:
         native.check(self.L.mis_set_sdf_contact(self._h, sdf._h, xf, bb, float(fd_eps), self._st()), "mis_set_sdf_contact")
         self._sdf = sdf          # keep the network alive while the scene uses it
 
+    def contact_force(self) -> torch.Tensor:
+        """Obstacle-contact force at the current frame's positions, (n,3), caller order."""
+        f = torch.empty((self.n, 3), device=self.device, dtype=torch.float32)
+        native.check(self.L.mis_get_contact_force(self._h, f.data_ptr(), self._st()), "mis_get_contact_force")
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        return f
+
+    def contact_counts(self):
+        """(broad-phase candidates, particles in the contact band) of the most recent step."""
+        c = (C.c_int * 2)(0, 0)
+        native.check(self.L.mis_get_contact_count(self._h, self._st(), c), "mis_get_contact_count")
+        return int(c[0]), int(c[1])
+
     def contact_count(self) -> int:
-        c = C.c_int(0)
-        native.check(self.L.mis_get_contact_count(self._h, self._st(), C.byref(c)), "mis_get_contact_count")
-        return int(c.value)
+        return self.contact_counts()[0]
 
     # ------------------------------------------------------------------ state export
     def position_velocity(self):

@@ -116,3 +116,39 @@ def test_plane_obstacle_equals_ground_penalty():
     # sdf = y is exact in the MLP up to fp32 rounding; the two runs differ by rounding of the contact force only,
     # amplified like any fp32 reordering (~1e-7 / ~1e-3 after a few hundred steps)
     assert (xa - xb).abs().max().item() < 3e-7 and (va - vb).abs().max().item() < 3e-3
+
+
+def test_octahedron_obstacle_contact_force_matches_oracle():
+    """Drop a sphere on an octahedron encoded in the reference architecture (9 layers); the contact force the step
+    applied at frame k must equal the oracle's contact law at the same positions, and the body must decelerate."""
+    from meshless_inflatable_softbody_b200 import Simulator
+    r_oct = 0.012
+    st = do.octahedron_state(r_oct, hidden=1024, n_linear=9)
+    net = _net(st)
+    cfg = SceneConfig()
+    x0, _ = scenes.jittered_sphere(3000, seed=0)
+    x0[:, 1] += (r_oct + 0.0004) - x0[:, 1].min()                        # lowest particle 0.4 mm above the tip
+    m = cfg.collision_range + 1e-3
+    sim = Simulator(x0, cfg)
+    sim.set_sdf_obstacle(net, bbox_model=[-r_oct - m, -r_oct - m, -r_oct - m, r_oct + m, r_oct + m, r_oct + m], fd_eps=1e-4)
+    sim.startup()
+    hit = False
+    for k in range(12):
+        sim.step(10)
+        x, v = sim.position_velocity()
+        f = sim.contact_force().cpu().numpy()
+        xn = x.cpu().numpy().astype(np.float64)
+        s0, gw, fo = do.contact_force(st, xn, np.eye(3), np.zeros(3), cfg.collision_penalty_stiffness, cfg.collision_range, 1e-4)
+        band = s0 < cfg.collision_range
+        # particles whose value sits within fp32 rounding of the band edge may fall on either side
+        sure = np.abs(s0 - cfg.collision_range) > 2e-7
+        assert np.array_equal((np.abs(f).sum(1) > 0)[sure], band[sure])
+        if band.any():
+            hit = True
+            scale = np.abs(fo).max()
+            # delta = range - sdf is known to ~1e-8 absolute (fp32 sdf at 0.01): relative force error 2 * 1e-8 / delta for the deepest
+            assert np.abs(f - fo)[sure].max() <= 2e-3 * scale + 1e-9, (np.abs(f - fo).max(), scale)
+        nb, nc = sim.contact_counts()
+        assert nb >= nc >= int(band[sure].sum()) - 2
+    assert hit
+    assert torch.isfinite(x).all()

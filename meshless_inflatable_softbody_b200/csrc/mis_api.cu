@@ -71,11 +71,11 @@ struct MisSim {
     float* stage = nullptr;           // n*6 device staging for host-buffer variants
     int cur = 0;
     bool built = false, mass_set = false, material_set = false, started = false, dirty = true;
+    bool forces_only = false;         // dirty because of fext / free_points alone: the stored elastic force is still valid
     long long launches = 0;
-    // CUDA graph cache for step chunks
-    cudaGraphExec_t graph_exec = nullptr;
-    int graph_steps = 0, graph_cur = -1;
-    long long graph_launches = 0;
+    // CUDA graph cache: one executable per (steps in the chunk, ping-pong index at its start)
+    struct StepGraph { cudaGraphExec_t exec = nullptr; int steps = 0, cur = -1; long long launches = 0; };
+    std::vector<StepGraph> graphs;
     cudaStream_t graph_stream = nullptr;
     // DeepSDF obstacle contact (extension)
     MisSdf* sdf = nullptr;
@@ -137,8 +137,8 @@ static View make_view(MisSim* s) {
 }
 
 static void drop_graph(MisSim* s) {
-    if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
-    s->graph_steps = 0; s->graph_cur = -1;
+    for (auto& g : s->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    s->graphs.clear();
 }
 
 // ------------------------------------------------------------------ create / destroy
@@ -385,7 +385,7 @@ extern "C" int mis_set_mass(MisSim* s, const float* mass_dev, void* stream) {
     if (s->G == 8) launch_volume<8>(s, st); else if (s->G == 16) launch_volume<16>(s, st); else launch_volume<32>(s, st);
     CK_LAUNCH();
     s->launches += 3;
-    s->mass_set = true; s->dirty = true;
+    s->mass_set = true; s->dirty = true; s->forces_only = false;
     return MIS_OK;
 }
 
@@ -393,7 +393,7 @@ extern "C" int mis_set_material(MisSim* s, const float* youngs_dev, const float*
     if (!s || !youngs_dev || !poisson_dev) return fail(MIS_E_INVALID, "null argument");
     k_material<<<nblk(s->n, 256), 256, 0, (cudaStream_t)stream>>>(youngs_dev, poisson_dev, s->perm, s->n, s->matl);
     CK_LAUNCH(); s->launches++;
-    s->material_set = true; s->dirty = true;
+    s->material_set = true; s->dirty = true; s->forces_only = false;
     return MIS_OK;
 }
 
@@ -401,7 +401,7 @@ extern "C" int mis_set_design(MisSim* s, const float* x_dev, void* stream) {
     if (!s || !x_dev) return fail(MIS_E_INVALID, "null argument");
     k_design<<<nblk(s->n, 256), 256, 0, (cudaStream_t)stream>>>(x_dev, s->perm, s->n, s->p.tanh_k, s->matl);
     CK_LAUNCH(); s->launches++;
-    s->dirty = true;
+    s->dirty = true; s->forces_only = false;
     return MIS_OK;
 }
 
@@ -409,7 +409,7 @@ extern "C" int mis_set_ext_force(MisSim* s, const float* f_dev, void* stream) {
     if (!s || !f_dev) return fail(MIS_E_INVALID, "null argument");
     k_gather_vec3<<<nblk(s->n, 256), 256, 0, (cudaStream_t)stream>>>(f_dev, s->perm, s->n, s->fext, 0);
     CK_LAUNCH(); s->launches++;
-    s->dirty = true;
+    if (!s->dirty) { s->dirty = true; s->forces_only = true; }
     return MIS_OK;
 }
 
@@ -423,7 +423,7 @@ extern "C" int mis_set_dirichlet(MisSim* s, const float* free_dev, void* stream)
     if (!s || !free_dev) return fail(MIS_E_INVALID, "null argument");
     k_gather_vec3<<<nblk(s->n, 256), 256, 0, (cudaStream_t)stream>>>(free_dev, s->perm, s->n, s->freem, 0);
     CK_LAUNCH(); s->launches++;
-    s->dirty = true;
+    if (!s->dirty) { s->dirty = true; s->forces_only = true; }
     return MIS_OK;
 }
 
@@ -479,18 +479,18 @@ static void enqueue_contact(MisSim* s, const View& v, cudaStream_t st) {
     if (!s->sdf) return;
     const int n = s->n;
     MisSdf* net = s->sdf;
-    cudaMemsetAsync(s->con_count, 0, 2 * sizeof(int), st);
+    cudaMemsetAsync(s->con_count, 0, 3 * sizeof(int), st);
     cudaMemsetAsync(s->fcon, 0, (size_t)n * sizeof(float4), st);
     k_contact_select<<<nblk(n, 256), 256, 0, st>>>(v.xcur, n, s->sdf_xf, s->sdf_lo, s->sdf_hi, s->con_idx, s->con_count, s->con_pts);
     const long long l0 = net->launches;
     sdf_forward(net, s->con_pts, nullptr, n, s->con_count, s->sdf_xf, make_float3(0.f, 0.f, 0.f), net->vals, st);
     k_contact_narrow<<<nblk(n, 256), 256, 0, st>>>(net->vals, s->con_idx, s->con_pts, s->con_count, s->p.col_range,
                                                    s->con_idx2, s->con_pts2, s->con_s0, s->con_count + 1);
+    // the three forward differences of the in-contact particles as ONE pass of 3 x count rows (row 3 r + axis);
+    // the chain's capacity is n rows, so at most n / 3 particles can be in the band at once (far more than a surface holds)
     const float e = s->sdf_eps;
-    const float3 shifts[3] = {make_float3(e, 0.f, 0.f), make_float3(0.f, e, 0.f), make_float3(0.f, 0.f, e)};
-    for (int q = 0; q < 3; q++)
-        sdf_forward(net, s->con_pts2, nullptr, n, s->con_count + 1, s->sdf_xf, shifts[q], net->vals + (size_t)(q + 1) * net->cap, st);
-    k_contact_apply<<<nblk(n, 256), 256, 0, st>>>(s->con_s0, net->vals + net->cap, net->cap, s->con_idx2, s->con_count + 1, 1.f / e, s->sdf_xf,
+    sdf_forward(net, s->con_pts2, nullptr, n, s->con_count + 2, s->sdf_xf, make_float3(e, 0.f, 0.f), net->vals + net->cap, st, 1);
+    k_contact_apply<<<nblk(n, 256), 256, 0, st>>>(s->con_s0, net->vals + net->cap, s->con_idx2, s->con_count + 1, n, 1.f / e, s->sdf_xf,
                                                   s->p.col_range, s->p.k_col, s->fcon);
     s->launches += 3 + (net->launches - l0);
 }
@@ -500,12 +500,19 @@ static int prime(MisSim* s, cudaStream_t st) {
     if (!s->mass_set || !s->material_set) return fail(MIS_E_STATE, "set_mass and set_material must precede startup/step");
     if (!s->p.euler) {
         View v = make_view(s);
-        enqueue_deform(s, v, st);
-        enqueue_contact(s, v, st);
-        enqueue_force(s, v, MODE_PRIME, st);
+        if (s->forces_only) {
+            // only the external force / Dirichlet mask changed (sim.py:279-286): the elastic and contact forces of the
+            // current frame are still valid; redo force_1 and part_1 (sim.py:247-251) per particle
+            k_reintegrate<<<nblk(s->n, 256), 256, 0, st>>>(v, s->c);
+            s->launches++;
+        } else {
+            enqueue_deform(s, v, st);
+            enqueue_contact(s, v, st);
+            enqueue_force(s, v, MODE_PRIME, st);
+        }
         CK_LAUNCH();
     }
-    s->dirty = false;
+    s->dirty = false; s->forces_only = false;
     return MIS_OK;
 }
 
@@ -515,7 +522,7 @@ extern "C" int mis_startup(MisSim* s, const float v0[3], void* stream) {
     s->cur = 0;
     k_startup<<<nblk(s->n, 256), 256, 0, st>>>(s->x0m, s->n, make_float3(v0[0], v0[1], v0[2]), s->xv[0], s->vel);
     CK_LAUNCH(); s->launches++;
-    s->started = true; s->dirty = true;
+    s->started = true; s->dirty = true; s->forces_only = false;
     return MIS_OK;
 }
 
@@ -525,7 +532,7 @@ extern "C" int mis_set_state(MisSim* s, const float* x_dev, const float* v_dev, 
     k_gather_vec3<<<nblk(s->n, 256), 256, 0, st>>>(x_dev, s->perm, s->n, s->xv[s->cur], 1);
     k_gather_vec3<<<nblk(s->n, 256), 256, 0, st>>>(v_dev, s->perm, s->n, s->vel, 0);
     CK_LAUNCH(); s->launches += 2;
-    s->started = true; s->dirty = true;
+    s->started = true; s->dirty = true; s->forces_only = false;
     return MIS_OK;
 }
 
@@ -546,38 +553,48 @@ static void enqueue_one_step(MisSim* s, cudaStream_t st) {
     }
 }
 
+static void enqueue_one_step(MisSim* s, cudaStream_t st);
+
+// launch `steps` steps as one cached CUDA graph (captured on first use for this ping-pong phase)
+static int launch_step_graph(MisSim* s, int steps, cudaStream_t st) {
+    if (s->graph_stream != st) { drop_graph(s); s->graph_stream = st; }
+    MisSim::StepGraph* hit = nullptr;
+    for (auto& g : s->graphs) if (g.steps == steps && g.cur == s->cur) hit = &g;
+    if (!hit) {
+        cudaGraph_t g = nullptr;
+        const long long l0 = s->launches;
+        const int cur0 = s->cur;
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        for (int k = 0; k < steps; k++) enqueue_one_step(s, st);
+        cudaError_t e = cudaStreamEndCapture(st, &g);
+        MisSim::StepGraph sg;
+        sg.steps = steps; sg.cur = cur0; sg.launches = s->launches - l0;
+        s->cur = cur0; s->launches = l0;
+        if (e != cudaSuccess) return fail(MIS_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&sg.exec, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(MIS_E_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+        s->graphs.push_back(sg);
+        hit = &s->graphs.back();
+    }
+    CK(cudaGraphLaunch(hit->exec, st));
+    s->launches += hit->launches;
+    if (steps & 1) s->cur ^= 1;                // an odd number of steps flips the ping-pong index
+    return MIS_OK;
+}
+
 extern "C" int mis_step(MisSim* s, int n_steps, void* stream) {
     if (!s || n_steps < 0) return fail(MIS_E_INVALID, "bad argument");
     if (!s->started) return fail(MIS_E_STATE, "mis_step before mis_startup / mis_set_state");
     cudaStream_t st = (cudaStream_t)stream;
     if (s->dirty) { int rc = prime(s, st); if (rc) return rc; }
     int chunk = s->p.graph_steps > 0 ? s->p.graph_steps : 32;
-    chunk &= ~1;                           // even: the ping-pong index returns to its start
     int done = 0;
-    const bool can_graph = st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
-    if (chunk >= 2 && s->p.graph_steps >= 0 && can_graph) {
-        while (n_steps - done >= chunk) {
-            if (!s->graph_exec || s->graph_steps != chunk || s->graph_cur != s->cur || s->graph_stream != st) {
-                drop_graph(s);
-                cudaGraph_t g = nullptr;
-                long long l0 = s->launches;
-                CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-                int cur0 = s->cur;
-                for (int k = 0; k < chunk; k++) enqueue_one_step(s, st);
-                cudaError_t e = cudaStreamEndCapture(st, &g);
-                s->cur = cur0;
-                s->graph_launches = s->launches - l0;
-                s->launches = l0;
-                if (e != cudaSuccess) return fail(MIS_E_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
-                e = cudaGraphInstantiate(&s->graph_exec, g, 0);
-                cudaGraphDestroy(g);
-                if (e != cudaSuccess) { s->graph_exec = nullptr; return fail(MIS_E_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e)); }
-                s->graph_steps = chunk; s->graph_cur = s->cur; s->graph_stream = st;
-            }
-            CK(cudaGraphLaunch(s->graph_exec, st));
-            s->launches += s->graph_launches;
-            done += chunk;                 // cur unchanged after an even number of steps
-        }
+    const bool can_graph = s->p.graph_steps >= 0 && st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+    if (can_graph) {
+        while (n_steps - done >= chunk) { int rc = launch_step_graph(s, chunk, st); if (rc) return rc; done += chunk; }
+        // the tail (and step(1) loops) go through single-step graphs: one launch instead of 2-40 per step
+        for (; done < n_steps; done++) { int rc = launch_step_graph(s, 1, st); if (rc) return rc; }
     }
     for (; done < n_steps; done++) enqueue_one_step(s, st);
     CK_LAUNCH();
@@ -639,7 +656,7 @@ extern "C" int mis_eval_forces(MisSim* s, const float* x_dev, float* fel_dev, vo
     k_export_vec3<<<nblk(s->n, 256), 256, 0, st>>>(s->scratch4 + s->n, s->inv_perm, s->n, fel_dev);
     s->launches++;
     CK_LAUNCH();
-    s->dirty = true;                      // R, S, F now describe x_dev, not the current frame
+    s->dirty = true; s->forces_only = false;                      // R, S, F now describe x_dev, not the current frame
     return MIS_OK;
 }
 
@@ -710,6 +727,7 @@ extern "C" int mis_sdf_create(int n_layers, const int* dims, const float* const*
     cudaStream_t st = (cudaStream_t)stream;
     MisSdf* s = new MisSdf();
     s->L = n_layers; s->H = H;
+    { int dev = 0, sms = 0; if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) s->num_sms = sms; }
 #define SALLOC(ptr, cnt) do { cudaError_t e_ = cudaMalloc((void**)&(ptr), (size_t)(cnt) * sizeof(float)); if (e_ != cudaSuccess) { int r_ = fail(MIS_E_CUDA, std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(e_)); sdf_free(s); return r_; } } while (0)
     SALLOC(s->W0, (size_t)H * 3); SALLOC(s->b0, H); SALLOC(s->wl, H); SALLOC(s->bl, 1);
     k_sdf_pack_weights<<<H, 256, 0, st>>>(g_dev[0], v_dev[0], H, 3, s->W0, nullptr, nullptr);
@@ -784,11 +802,12 @@ extern "C" int mis_sdf_profile_gemm(MisSdf* s, int m, int reps, void* stream, do
     CK(cudaMemsetAsync(s->act[0][1], 0, (size_t)m_pad * s->H * sizeof(float), st));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    dim3 grid(s->H / SDF_BN, m_pad / SDF_BM);
-    k_sdf_gemm<<<grid, SDF_THREADS, SDF_SMEM_BYTES, st>>>(s->act[0][0], s->act[0][1], s->Whi[0], s->Wlo[0], s->bh[0], s->H, s->H, s->act[1][0], s->act[1][1], nullptr);
+    const int tiles = (s->H / SDF_BN) * (m_pad / SDF_BM);
+    const int grid = tiles < s->num_sms ? tiles : s->num_sms;
+    k_sdf_gemm<<<grid, SDF_THREADS, SDF_SMEM_BYTES, st>>>(s->act[0][0], s->act[0][1], s->Whi[0], s->Wlo[0], s->bh[0], s->H, s->H, s->act[1][0], s->act[1][1], m_pad, nullptr);
     CK(cudaEventRecord(e0, st));
     for (int r = 0; r < reps; r++)
-        k_sdf_gemm<<<grid, SDF_THREADS, SDF_SMEM_BYTES, st>>>(s->act[0][0], s->act[0][1], s->Whi[0], s->Wlo[0], s->bh[0], s->H, s->H, s->act[1][0], s->act[1][1], nullptr);
+        k_sdf_gemm<<<grid, SDF_THREADS, SDF_SMEM_BYTES, st>>>(s->act[0][0], s->act[0][1], s->Whi[0], s->Wlo[0], s->bh[0], s->H, s->H, s->act[1][0], s->act[1][1], m_pad, nullptr);
     CK(cudaEventRecord(e1, st));
     CK(cudaStreamSynchronize(st));
     float ms = 0.f;
@@ -803,7 +822,7 @@ extern "C" int mis_sdf_profile_gemm(MisSdf* s, int m, int reps, void* stream, do
 extern "C" int mis_set_sdf_contact(MisSim* s, MisSdf* sdf, const float* xform_host, const float* bbox_host, float fd_eps, void* stream) {
     if (!s) return fail(MIS_E_INVALID, "null sim");
     drop_graph(s);
-    s->dirty = true;
+    s->dirty = true; s->forces_only = false;
     if (!sdf) { s->sdf = nullptr; return MIS_OK; }
     if (!bbox_host || !(fd_eps > 0.f)) return fail(MIS_E_INVALID, "mis_set_sdf_contact: bbox and a positive fd_eps are required");
     const size_t N = (size_t)s->n;

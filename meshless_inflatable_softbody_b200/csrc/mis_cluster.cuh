@@ -561,6 +561,13 @@ __global__ void __launch_bounds__(STEP_THREADS, MIS_STEP_MIN_BLOCKS) k_force_c(V
     }
 }
 
+// force_1 + part_1 again from the stored elastic force (external force or Dirichlet mask changed between steps)
+__global__ void __launch_bounds__(256) k_reintegrate(View s, Consts c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n) return;
+    integrate_epilogue(s, c, i, xyz(s.fel[i]), MODE_PRIME, s.x0m[i], s.xcur[i]);
+}
+
 // ---------------------------------------------------------------- small per-particle kernels
 // gather caller-order arrays into cell-sorted slots
 __global__ void __launch_bounds__(256) k_gather_vec3(const float* __restrict__ src, const uint32_t* __restrict__ perm, int n, float4* __restrict__ dst, int keep_w) {

@@ -30,7 +30,7 @@ constexpr int SDF_TILE_FLOATS = 128 * 32;                    // one 128 x 32 fp3
 constexpr int SDF_TILE_BYTES = SDF_TILE_FLOATS * 4;          // 16 KB
 constexpr int SDF_STAGES = 2;
 constexpr int SDF_STAGE_BYTES = 6 * SDF_TILE_BYTES;          // A_hi, A_lo, B_hi[2], B_lo[2]
-constexpr int SDF_SMEM_BYTES = SDF_STAGES * SDF_STAGE_BYTES + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int SDF_SMEM_BYTES = SDF_STAGES * SDF_STAGE_BYTES + 256 /*barriers*/ + 1024 /*align*/;
 constexpr int SDF_THREADS = 192;
 
 __host__ __device__ __forceinline__ size_t sdf_tile_off(int r, int k, int KB) {
@@ -93,36 +93,52 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256
 constexpr uint32_t SDF_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SDF_BN >> 3) << 17) | ((uint32_t)(SDF_BM >> 4) << 24);
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // ---------------------------------------------------------------- the hidden layer
-// Yhi/Ylo[M_pad, N] = split( relu( (Xhi + Xlo)[M_pad, K] (Whi + Wlo)[N, K]^T + bias ) ), all matrices in UMMA tiles.
-// grid = (N / 256, M_pad / 128): n fastest so the CTAs of one row-block run together and share A in L2.
+// Yhi/Ylo[M, N] = split( relu( (Xhi + Xlo)[M, K] (Whi + Wlo)[N, K]^T + bias ) ), all matrices in UMMA tiles.
+// Persistent: gridDim.x CTAs (one per SM) walk the 128 x 256 output tiles t = blockIdx.x, + gridDim.x, ... with
+// t -> (row-block t / NT, column-block t % NT), so the CTAs running together share A row-blocks and W in L2.  The number
+// of live rows may sit on the device (m_count): no host synchronisation is needed to size the work.
+// The accumulator is double-buffered in TMEM (2 x 256 columns): the epilogue of tile i overlaps the MMAs of tile i+1.
 __global__ void __launch_bounds__(SDF_THREADS, 1) k_sdf_gemm(const float* __restrict__ Xhi, const float* __restrict__ Xlo,
                                                              const float* __restrict__ Whi, const float* __restrict__ Wlo,
                                                              const float* __restrict__ bias, int K, int N,
                                                              float* __restrict__ Yhi, float* __restrict__ Ylo,
-                                                             const int* __restrict__ m_count /* device-side row count, may be null */) {
+                                                             int m_rows, const int* __restrict__ m_count /* device-side live rows, may be null */) {
     extern __shared__ uint8_t smem_raw[];
-    const int nb = blockIdx.x, mb = blockIdx.y;
-    if (m_count && mb * SDF_BM >= *m_count) return;          // nothing to do for row-blocks past the live rows
+    const int live = m_count ? min(*m_count, m_rows) : m_rows;
+    const int row_blocks = (live + SDF_BM - 1) / SDF_BM;
+    // few live rows (per-step contact queries): 64-wide column tiles spread one row-block over 16 CTAs instead of 4, which
+    // cuts the latency of a layer ~4x; many rows: 256-wide tiles (best operand reuse).  Uniform across the grid.
+    const int bn = (row_blocks * (N / SDF_BN) * 2 <= (int)gridDim.x) ? 64 : SDF_BN;
+    const int NT = N / bn;
+    const int total = row_blocks * NT;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(SDF_BM >> 4) << 24);
+    const uint32_t b_bytes = (uint32_t)bn * SDF_BK * 4;              // one B plane (hi or lo) of this tile
+    const uint32_t stage_bytes = 2 * SDF_TILE_BYTES + 2 * b_bytes;   // A_hi, A_lo, B_hi, B_lo
+    const uint32_t stages = (bn == SDF_BN) ? 2u : 4u;                // 2 x 96 KB or 4 x 48 KB: deeper ring when the MMAs are short
+    const uint32_t off_bhi = 2 * SDF_TILE_BYTES, off_blo = 2 * SDF_TILE_BYTES + b_bytes;
+    if ((int)blockIdx.x >= total) return;                    // uniform per CTA: nothing allocated yet
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KB = K / SDF_BK;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bias_s = base + SDF_STAGES * SDF_STAGE_BYTES;
-    const uint32_t bars = bias_s + 1024;
-    // full[s] at bars + 8 s, empty[s] at bars + 16 + 8 s, tmem_full at bars + 32, tmem pointer at bars + 40
-    float* bias_sm = reinterpret_cast<float*>(smem_raw + (bias_s - smem_u32(smem_raw)));
-    volatile uint32_t* tmem_ptr_sm = reinterpret_cast<volatile uint32_t*>(smem_raw + (bars + 40 - smem_u32(smem_raw)));
+    const uint32_t bars = base + SDF_STAGES * SDF_STAGE_BYTES;
+    // full[s] +8 s | empty[s] +32 + 8 s (s < 4) | tmem_full[b] +64 + 8 b | tmem_empty[b] +80 + 8 b | tmem pointer +96
+    const uint32_t BAR_EMPTY = bars + 32, BAR_TFULL = bars + 64, BAR_TEMPTY = bars + 80, TMEM_SLOT = bars + 96;
+    volatile uint32_t* tmem_ptr_sm = reinterpret_cast<volatile uint32_t*>(smem_raw + (TMEM_SLOT - smem_u32(smem_raw)));
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < SDF_STAGES; s++) { mbar_init(bars + 8 * s, 1); mbar_init(bars + 16 + 8 * s, 1); }
-        mbar_init(bars + 32, 1);
+        for (int s = 0; s < 4; s++) { mbar_init(bars + 8 * s, 1); mbar_init(BAR_EMPTY + 8 * s, 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(BAR_TFULL + 8 * b, 1); mbar_init(BAR_TEMPTY + 8 * b, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars + 40), "r"(256u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(TMEM_SLOT), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int t = threadIdx.x; t < SDF_BN; t += SDF_THREADS) bias_sm[t] = bias[nb * SDF_BN + t];
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -130,83 +146,111 @@ __global__ void __launch_bounds__(SDF_THREADS, 1) k_sdf_gemm(const float* __rest
 
     if (warp == 0) {
         if (lane == 0) {
-            const float* a_hi = Xhi + (size_t)mb * KB * SDF_TILE_FLOATS;
-            const float* a_lo = Xlo + (size_t)mb * KB * SDF_TILE_FLOATS;
-            const float* b_hi0 = Whi + (size_t)(2 * nb) * KB * SDF_TILE_FLOATS;
-            const float* b_hi1 = Whi + (size_t)(2 * nb + 1) * KB * SDF_TILE_FLOATS;
-            const float* b_lo0 = Wlo + (size_t)(2 * nb) * KB * SDF_TILE_FLOATS;
-            const float* b_lo1 = Wlo + (size_t)(2 * nb + 1) * KB * SDF_TILE_FLOATS;
-            for (int kb = 0; kb < KB; kb++) {
-                const int s = kb % SDF_STAGES;
-                const uint32_t ph = (kb / SDF_STAGES) & 1;
-                mbar_wait(bars + 16 + 8 * s, ph ^ 1);               // slot free (first pass returns at once)
-                const uint32_t full = bars + 8 * s;
-                mbar_expect_tx(full, SDF_STAGE_BYTES);
-                const uint32_t st = base + s * SDF_STAGE_BYTES;
-                const size_t o = (size_t)kb * SDF_TILE_FLOATS;
-                tma_bulk_g2s(st + 0 * SDF_TILE_BYTES, a_hi + o, SDF_TILE_BYTES, full);
-                tma_bulk_g2s(st + 1 * SDF_TILE_BYTES, a_lo + o, SDF_TILE_BYTES, full);
-                tma_bulk_g2s(st + 2 * SDF_TILE_BYTES, b_hi0 + o, SDF_TILE_BYTES, full);
-                tma_bulk_g2s(st + 3 * SDF_TILE_BYTES, b_hi1 + o, SDF_TILE_BYTES, full);
-                tma_bulk_g2s(st + 4 * SDF_TILE_BYTES, b_lo0 + o, SDF_TILE_BYTES, full);
-                tma_bulk_g2s(st + 5 * SDF_TILE_BYTES, b_lo1 + o, SDF_TILE_BYTES, full);
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int mb = t / NT, nb = t - mb * NT;
+                const float* a_hi = Xhi + (size_t)mb * KB * SDF_TILE_FLOATS;
+                const float* a_lo = Xlo + (size_t)mb * KB * SDF_TILE_FLOATS;
+                // W rows [bn nb, bn nb + bn): two whole 128-row tiles (bn = 256) or half of one (bn = 64: 8 row-groups = 8 KB contiguous)
+                const int n0 = nb * bn;
+                const size_t wrow = (size_t)(n0 >> 7) * KB * SDF_TILE_FLOATS + (size_t)((n0 & 127) >> 3) * 256;
+                const float* b_hi0 = Whi + wrow;
+                const float* b_lo0 = Wlo + wrow;
+                const float* b_hi1 = b_hi0 + (size_t)KB * SDF_TILE_FLOATS;
+                const float* b_lo1 = b_lo0 + (size_t)KB * SDF_TILE_FLOATS;
+                for (int kb = 0; kb < KB; kb++, it++) {
+                    const uint32_t s = it % stages, ph = (it / stages) & 1;
+                    mbar_wait(BAR_EMPTY + 8 * s, ph ^ 1);               // slot free (first pass returns at once)
+                    const uint32_t full = bars + 8 * s;
+                    mbar_expect_tx(full, stage_bytes);
+                    const uint32_t st = base + s * stage_bytes;
+                    const size_t o = (size_t)kb * SDF_TILE_FLOATS;
+                    tma_bulk_g2s(st + 0 * SDF_TILE_BYTES, a_hi + o, SDF_TILE_BYTES, full);
+                    tma_bulk_g2s(st + 1 * SDF_TILE_BYTES, a_lo + o, SDF_TILE_BYTES, full);
+                    if (bn == SDF_BN) {
+                        tma_bulk_g2s(st + off_bhi, b_hi0 + o, SDF_TILE_BYTES, full);
+                        tma_bulk_g2s(st + off_bhi + SDF_TILE_BYTES, b_hi1 + o, SDF_TILE_BYTES, full);
+                        tma_bulk_g2s(st + off_blo, b_lo0 + o, SDF_TILE_BYTES, full);
+                        tma_bulk_g2s(st + off_blo + SDF_TILE_BYTES, b_lo1 + o, SDF_TILE_BYTES, full);
+                    } else {
+                        tma_bulk_g2s(st + off_bhi, b_hi0 + o, b_bytes, full);
+                        tma_bulk_g2s(st + off_blo, b_lo0 + o, b_bytes, full);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            for (int kb = 0; kb < KB; kb++) {
-                const int s = kb % SDF_STAGES;
-                const uint32_t ph = (kb / SDF_STAGES) & 1;
-                mbar_wait(bars + 8 * s, ph);                         // operands landed
+            uint32_t it = 0, lt = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, lt++) {
+                const uint32_t b = lt & 1;
+                mbar_wait(BAR_TEMPTY + 8 * b, ((lt >> 1) & 1) ^ 1);      // epilogue has drained this accumulator buffer
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t st = base + s * SDF_STAGE_BYTES;
+                const uint32_t acc = tmem_acc + b * SDF_BN;
+                for (int kb = 0; kb < KB; kb++, it++) {
+                    const uint32_t s = it % stages, ph = (it / stages) & 1;
+                    mbar_wait(bars + 8 * s, ph);                         // operands landed
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = base + s * stage_bytes;
 #pragma unroll
-                for (int ks = 0; ks < SDF_BK / 8; ks++) {
-                    const uint32_t ko = ks * 256;                    // 8 floats along K = 2 core matrices = 256 B
-                    const uint64_t ahi = umma_desc(st + 0 * SDF_TILE_BYTES + ko), alo = umma_desc(st + 1 * SDF_TILE_BYTES + ko);
-                    const uint64_t bhi = umma_desc(st + 2 * SDF_TILE_BYTES + ko), blo = umma_desc(st + 4 * SDF_TILE_BYTES + ko);
-                    umma_tf32(tmem_acc, alo, bhi, SDF_IDESC, (kb | ks) ? 1u : 0u);
-                    umma_tf32(tmem_acc, ahi, blo, SDF_IDESC, 1u);
-                    umma_tf32(tmem_acc, ahi, bhi, SDF_IDESC, 1u);
+                    for (int ks = 0; ks < SDF_BK / 8; ks++) {
+                        const uint32_t ko = ks * 256;                    // 8 floats along K = 2 core matrices = 256 B
+                        const uint64_t ahi = umma_desc(st + 0 * SDF_TILE_BYTES + ko), alo = umma_desc(st + 1 * SDF_TILE_BYTES + ko);
+                        const uint64_t bhi = umma_desc(st + off_bhi + ko), blo = umma_desc(st + off_blo + ko);
+                        umma_tf32(acc, alo, bhi, idesc, (kb | ks) ? 1u : 0u);
+                        umma_tf32(acc, ahi, blo, idesc, 1u);
+                        umma_tf32(acc, ahi, bhi, idesc, 1u);
+                    }
+                    umma_commit(BAR_EMPTY + 8 * s);                      // frees the smem stage when these MMAs retire
                 }
-                umma_commit(bars + 16 + 8 * s);                      // frees the smem stage when these MMAs retire
+                umma_commit(BAR_TFULL + 8 * b);                          // accumulator complete
             }
-            umma_commit(bars + 32);                                   // accumulator complete
         }
     } else {
         // epilogue: warp w may touch TMEM lanes [32 (w % 4), 32 (w % 4) + 32)
         const int q = warp & 3;
-        mbar_wait(bars + 32, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int rl = 32 * q + lane;                                 // row inside the 128-row block
         const int KBn = N / SDF_BK;                                   // k-blocks of the NEXT layer's A operand
         const size_t row_off = (size_t)(rl >> 3) * 256 + (rl & 7) * 4;
+        uint32_t lt = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, lt++) {
+            const int mb = t / NT, nb = t - mb * NT;
+            const uint32_t b = lt & 1;
+            mbar_wait(BAR_TFULL + 8 * b, (lt >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-        for (int c = 0; c < SDF_BN; c += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
-            const size_t tile = ((size_t)mb * KBn + (size_t)(nb * SDF_BN + c) / SDF_BK) * SDF_TILE_FLOATS + row_off;
-            float4* dhi = reinterpret_cast<float4*>(Yhi + tile);
-            float4* dlo = reinterpret_cast<float4*>(Ylo + tile);
+            for (int c = 0; c < bn; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_acc + ((uint32_t)(32 * q) << 16) + b * SDF_BN + (uint32_t)c, v);
+                const size_t tile = ((size_t)mb * KBn + (size_t)(nb * bn + c) / SDF_BK) * SDF_TILE_FLOATS + row_off;
+                float4* dhi = reinterpret_cast<float4*>(Yhi + tile);
+                float4* dlo = reinterpret_cast<float4*>(Ylo + tile);
+                const float4* bp = reinterpret_cast<const float4*>(bias + nb * bn + c);
 #pragma unroll
-            for (int kc = 0; kc < 8; kc++) {
-                float h[4], l[4];
+                for (int kc = 0; kc < 8; kc++) {
+                    const float4 bb = __ldg(bp + kc);                 // same address in every lane: one broadcast load
+                    const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+                    float h[4], l[4];
 #pragma unroll
-                for (int e = 0; e < 4; e++) {
-                    const float y = fmaxf(__uint_as_float(v[4 * kc + e]) + bias_sm[c + 4 * kc + e], 0.f);
-                    h[e] = tf32_hi(y);
-                    l[e] = y - h[e];
+                    for (int e = 0; e < 4; e++) {
+                        const float y = fmaxf(__uint_as_float(v[4 * kc + e]) + bv[e], 0.f);
+                        h[e] = tf32_hi(y);
+                        l[e] = y - h[e];
+                    }
+                    dhi[kc * 8] = make_float4(h[0], h[1], h[2], h[3]);    // next core matrix along K: +32 floats = 8 float4
+                    dlo[kc * 8] = make_float4(l[0], l[1], l[2], l[3]);
                 }
-                dhi[kc * 8] = make_float4(h[0], h[1], h[2], h[3]);    // next core matrix along K: +32 floats = 8 float4
-                dlo[kc * 8] = make_float4(l[0], l[1], l[2], l[3]);
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR_TEMPTY + 8 * b);            // this warp is done reading the buffer
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(512u) : "memory");
     }
 }
 
@@ -248,48 +292,52 @@ __global__ void __launch_bounds__(256) k_sdf_pack_weights(const float* __restric
 // One thread per (row, 4 consecutive outputs) = one 16-byte chunk of the hi and lo tiles.
 struct SdfXform { float A[9]; float t[3]; };
 
+// fd3 != 0: row r evaluates point r / 3 displaced by `shift.x` along model axis r % 3 (the three forward differences in one pass).
 __global__ void __launch_bounds__(256) k_sdf_layer0(const float* __restrict__ pts, const int* __restrict__ idx, int m, int m_pad,
-                                                    const int* __restrict__ m_count, SdfXform xf, float3 shift,
+                                                    const int* __restrict__ m_count, SdfXform xf, float3 shift0, int fd3,
                                                     const float* __restrict__ W0 /* [H,3] */, const float* __restrict__ b0, int H,
                                                     float* __restrict__ Yhi, float* __restrict__ Ylo) {
     const int chunks = H / 4;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = (int)(gid / chunks), ch = (int)(gid % chunks);
-    if (r >= m_pad) return;
     const int live = m_count ? min(*m_count, m) : m;
-    if (m_count && (r & ~127) >= live) return;
-    float x = 0.f, y = 0.f, z = 0.f;
-    if (r < live) {
-        const int src = idx ? idx[r] : r;
-        const float px = pts[3 * (size_t)src] - xf.t[0], py = pts[3 * (size_t)src + 1] - xf.t[1], pz = pts[3 * (size_t)src + 2] - xf.t[2];
-        x = xf.A[0] * px + xf.A[1] * py + xf.A[2] * pz + shift.x;
-        y = xf.A[3] * px + xf.A[4] * py + xf.A[5] * pz + shift.y;
-        z = xf.A[6] * px + xf.A[7] * py + xf.A[8] * pz + shift.z;
-    }
-    float h[4], l[4];
+    const long long work = (long long)((live + 127) & ~127) * chunks;        // whole row-blocks: the GEMM reads 128-row tiles
+    for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < work; gid += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(gid / chunks), ch = (int)(gid % chunks);
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (r < live) {
+            const int pr = fd3 ? r / 3 : r;
+            const int src = idx ? idx[pr] : pr;
+            float3 shift = shift0;
+            if (fd3) { const int a = r - 3 * pr; shift = make_float3(a == 0 ? shift0.x : 0.f, a == 1 ? shift0.x : 0.f, a == 2 ? shift0.x : 0.f); }
+            const float px = pts[3 * (size_t)src] - xf.t[0], py = pts[3 * (size_t)src + 1] - xf.t[1], pz = pts[3 * (size_t)src + 2] - xf.t[2];
+            x = xf.A[0] * px + xf.A[1] * py + xf.A[2] * pz + shift.x;
+            y = xf.A[3] * px + xf.A[4] * py + xf.A[5] * pz + shift.y;
+            z = xf.A[6] * px + xf.A[7] * py + xf.A[8] * pz + shift.z;
+        }
+        float h[4], l[4];
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-        const int o = 4 * ch + e;
-        // nn.Linear: x W^T + b, accumulated in k order like a dot product
-        float acc = x * W0[3 * o];
-        acc = fmaf(y, W0[3 * o + 1], acc);
-        acc = fmaf(z, W0[3 * o + 2], acc);
-        acc = fmaxf(acc + b0[o], 0.f);
-        h[e] = tf32_hi(acc); l[e] = acc - h[e];
+        for (int e = 0; e < 4; e++) {
+            const int o = 4 * ch + e;
+            // nn.Linear: x W^T + b, accumulated in k order like a dot product
+            float acc = x * W0[3 * o];
+            acc = fmaf(y, W0[3 * o + 1], acc);
+            acc = fmaf(z, W0[3 * o + 2], acc);
+            acc = fmaxf(acc + b0[o], 0.f);
+            h[e] = tf32_hi(acc); l[e] = acc - h[e];
+        }
+        const size_t off = sdf_tile_off(r, 4 * ch, H / SDF_BK);
+        *reinterpret_cast<float4*>(Yhi + off) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(Ylo + off) = make_float4(l[0], l[1], l[2], l[3]);
     }
-    const size_t off = sdf_tile_off(r, 4 * ch, H / SDF_BK);
-    *reinterpret_cast<float4*>(Yhi + off) = make_float4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<float4*>(Ylo + off) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
 // ---------------------------------------------------------------- last layer: Linear(H, 1) on CUDA cores
 // One warp per row; lane = k-block, fixed summation order (deterministic).
 __global__ void __launch_bounds__(256) k_sdf_last(const float* __restrict__ Xhi, const float* __restrict__ Xlo, int m, const int* __restrict__ m_count,
                                                   const float* __restrict__ w /* [H] */, const float* __restrict__ b, int H, float* __restrict__ out) {
-    const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     const int live = m_count ? min(*m_count, m) : m;
-    if (r >= live) return;
     const int KB = H / SDF_BK;
+    for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < live; r += gridDim.x * 8) {
     float acc = 0.f;
     for (int kb = lane; kb < KB; kb += 32) {
         const size_t base = ((size_t)(r >> 7) * KB + kb) * SDF_TILE_FLOATS + ((r & 127) >> 3) * 256 + (r & 7) * 4;
@@ -305,6 +353,7 @@ __global__ void __launch_bounds__(256) k_sdf_last(const float* __restrict__ Xhi,
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
     if (lane == 0) out[r] = acc + b[0];
+    }
 }
 
 }  // namespace mis

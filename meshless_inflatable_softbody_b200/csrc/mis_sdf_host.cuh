@@ -16,6 +16,7 @@ struct MisSdf {
     float *vals = nullptr;     // 4 x cap scalars: sdf at p, p+eps ex, p+eps ey, p+eps ez
     long long launches = 0;
     long long gemm_launches = 0;
+    int num_sms = 148;         // persistent GEMM grid: one CTA per SM
 };
 
 namespace mis {
@@ -50,7 +51,7 @@ inline cudaError_t sdf_reserve(MisSdf* s, int rows) {
 // One forward pass of the chain for `rows` points (rows <= cap): points -> out[rows].
 //   pts/idx: point r is pts[idx ? idx[r] : r]; xf/shift: p_model = A (p - t) + shift; m_count: optional device-side live-row count.
 inline cudaError_t sdf_forward(MisSdf* s, const float* pts, const int* idx, int rows, const int* m_count, const SdfXform& xf, float3 shift,
-                               float* out, cudaStream_t st) {
+                               float* out, cudaStream_t st, int fd3 = 0) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_sdf_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES);
@@ -60,17 +61,19 @@ inline cudaError_t sdf_forward(MisSdf* s, const float* pts, const int* idx, int 
     const int m_pad = (rows + 127) / 128 * 128;
     const int H = s->H;
     const long long threads0 = (long long)m_pad * (H / 4);
-    k_sdf_layer0<<<(unsigned)((threads0 + 255) / 256), 256, 0, st>>>(pts, idx, rows, m_pad, m_count, xf, shift, s->W0, s->b0, H, s->act[0][0], s->act[0][1]);
+    const long long blocks0 = (threads0 + 255) / 256;
+    k_sdf_layer0<<<(unsigned)(blocks0 < 148 * 16 ? blocks0 : 148 * 16), 256, 0, st>>>(pts, idx, rows, m_pad, m_count, xf, shift, fd3, s->W0, s->b0, H, s->act[0][0], s->act[0][1]);
     s->launches++;
     int cur = 0;
     for (size_t l = 0; l < s->Whi.size(); l++) {
-        dim3 grid(H / SDF_BN, m_pad / SDF_BM);
-        k_sdf_gemm<<<grid, SDF_THREADS, SDF_SMEM_BYTES, st>>>(s->act[cur][0], s->act[cur][1], s->Whi[l], s->Wlo[l], s->bh[l], H, H,
-                                                              s->act[cur ^ 1][0], s->act[cur ^ 1][1], m_count);
+        const int tiles = (H / SDF_BN) * (m_pad / SDF_BM);
+        k_sdf_gemm<<<tiles < s->num_sms ? tiles : s->num_sms, SDF_THREADS, SDF_SMEM_BYTES, st>>>(
+            s->act[cur][0], s->act[cur][1], s->Whi[l], s->Wlo[l], s->bh[l], H, H, s->act[cur ^ 1][0], s->act[cur ^ 1][1], rows, m_count);
         s->launches++; s->gemm_launches++;
         cur ^= 1;
     }
-    k_sdf_last<<<(rows + 7) / 8, 256, 0, st>>>(s->act[cur][0], s->act[cur][1], rows, m_count, s->wl, s->bl, H, out);
+    const int blocksl = (rows + 7) / 8;
+    k_sdf_last<<<blocksl < 148 * 8 ? blocksl : 148 * 8, 256, 0, st>>>(s->act[cur][0], s->act[cur][1], rows, m_count, s->wl, s->bl, H, out);
     s->launches++;
     return cudaGetLastError();
 }
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(256) k_contact_narrow(const float* __restrict_
     if (m == 0) return;
     const int lane = threadIdx.x & 31;
     int basep = 0;
-    if (lane == __ffs(m) - 1) basep = atomicAdd(count2, __popc(m));
+    if (lane == __ffs(m) - 1) { basep = atomicAdd(count2, __popc(m)); atomicAdd(count2 + 1, 3 * __popc(m)); }   // [1] = rows of the FD pass
     basep = __shfl_sync(0xffffffffu, basep, __ffs(m) - 1);
     if (in) {
         const int q = basep + __popc(m & ((1u << lane) - 1));
@@ -137,14 +140,14 @@ __global__ void __launch_bounds__(256) k_contact_narrow(const float* __restrict_
 }
 
 // contact law: delta = range - sdf(p_model); f = delta^2 k n, n = grad / |grad| in world space.
-// fd holds the three forward-difference evaluations of the in-contact particles (planes of `cap`).
-__global__ void __launch_bounds__(256) k_contact_apply(const float* __restrict__ s0c, const float* __restrict__ fd, int cap, const int* __restrict__ idx2,
-                                                       const int* __restrict__ count2, float inv_eps, SdfXform xf, float range, float k_col,
+// fd holds the three forward-difference evaluations of the in-contact particles, interleaved (3 r + axis).
+__global__ void __launch_bounds__(256) k_contact_apply(const float* __restrict__ s0c, const float* __restrict__ fd, const int* __restrict__ idx2,
+                                                       const int* __restrict__ count2, int fd_rows, float inv_eps, SdfXform xf, float range, float k_col,
                                                        float4* __restrict__ fcon) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= *count2) return;
+    if (r >= *count2 || 3 * r + 2 >= fd_rows) return;      // fd_rows = rows the FD pass could evaluate
     const float s0 = s0c[r];
-    const float gx = (fd[r] - s0) * inv_eps, gy = (fd[(size_t)cap + r] - s0) * inv_eps, gz = (fd[2 * (size_t)cap + r] - s0) * inv_eps;
+    const float gx = (fd[3 * (size_t)r] - s0) * inv_eps, gy = (fd[3 * (size_t)r + 1] - s0) * inv_eps, gz = (fd[3 * (size_t)r + 2] - s0) * inv_eps;
     float wx = xf.A[0] * gx + xf.A[3] * gy + xf.A[6] * gz;
     float wy = xf.A[1] * gx + xf.A[4] * gy + xf.A[7] * gz;
     float wz = xf.A[2] * gx + xf.A[5] * gy + xf.A[8] * gz;

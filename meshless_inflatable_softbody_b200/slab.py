@@ -210,6 +210,13 @@ class SlabSimulator:
             self._exchange()
         self.frame += int(n_steps)
 
+    def set_external_forces_host(self, f_host):
+        """Per-step input path for the local particles (owned + ghosts): part_1 is redone with the new force and the
+        ghosts' new positions are exchanged again."""
+        self.sim.set_external_forces_host(f_host)
+        self.sim.step(0)
+        self._exchange()
+
     def position_velocity(self):
         """(x, v) of the OWNED particles, in the order of plan.owned (ascending global id)."""
         x, v = self.sim.position_velocity()

@@ -283,3 +283,22 @@ def test_export_targets_format(tmp_path, sphere800):
         p = np.load(tmp_path / f"position_{i}.npy"); v = np.load(tmp_path / f"velocity_{i}.npy")
         assert p.shape == (len(sphere800), 3) and p.dtype == np.float32 and v.shape == p.shape
     assert sim.frame == 15
+
+
+def test_force_change_takes_the_cheap_path_and_equals_a_full_reprime(sphere3k):
+    """Changing only the external force between steps (sim.py:279-283) redoes force_1 / part_1 from the stored elastic
+    force; the result must equal a full re-evaluation (forced here by re-sending the design field)."""
+    a, b = _sim(sphere3k), _sim(sphere3k)
+    a.startup(); b.startup()
+    a.step(20); b.step(20)
+    f = np.tile(np.float32([3e-4, -1e-3, 0.0]), (len(sphere3k), 1))
+    la = a.launch_count
+    a.set_external_forces(f); a.step(1)
+    cheap = a.launch_count - la
+    lb = b.launch_count
+    b.set_external_forces(f); b.set_design(SceneConfig().design_x); b.step(1)
+    full = b.launch_count - lb
+    assert cheap < full
+    a.step(15); b.step(15)
+    xa, va = a.position_velocity(); xb, vb = b.position_velocity()
+    assert torch.equal(xa, xb) and torch.equal(va, vb)

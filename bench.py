@@ -108,13 +108,9 @@ def sphere_on_obstacle(n, seed):
 
 
 def beam_scene(n_total, seed, world):
-    """Beam with its long axis along x: cross-section fixed, length proportional to the particle count."""
+    """One elongated body (ellipsoid, long axis x, ~1.6 radii of length per GPU) falling freely above the ground plane."""
     from meshless_inflatable_softbody_b200 import scenes
-    h, s = 0.007, 0.5 * 0.007
-    side = 40 * s                                            # 40 x 40 lattice sites in the cross-section
-    length = n_total * s ** 3 / side ** 2
-    x0 = scenes.jittered_beam(n_total, seed=seed, aspect=(length / side, 1.0, 1.0), centre=(0.0, 0.0, 0.0))
-    x0[:, 1] += 0.0006 - x0[:, 1].min()                      # low drop onto the ground plane
+    x0 = scenes.jittered_ellipsoid(n_total, seed=seed, aspect=(1.6 * max(world, 1), 1.0, 1.0), low_drop=True)
     return x0.astype(np.float32)
 
 
@@ -159,9 +155,9 @@ def workload_config(args, n_total, mean_k, world, mode, extra=None):
     elif mode == "batch":
         wl = "BASELINE configs[3] shape: independent ~%d-particle scenes, one per GPU, no communication" % args.n
     elif mode == "strong":
-        wl = "BASELINE configs[4] shape: one %d-particle beam slab-partitioned across %d GPUs, NCCL halo exchange per step" % (n_total, world)
+        wl = "BASELINE configs[4] shape: one %d-particle elongated body slab-partitioned across %d GPUs, NCCL halo exchange per step" % (n_total, world)
     else:
-        wl = ("one %d-particle beam (%d per GPU) slab-partitioned across %d GPUs, NCCL halo exchange of ghost positions "
+        wl = ("one %d-particle elongated body (%d per GPU) slab-partitioned across %d GPUs, NCCL halo exchange of ghost positions "
               "every step (BASELINE configs[4] mechanism at fixed per-GPU size)" % (n_total, args.n, world))
     c = {"workload": wl, "n_particles": int(n_total), "mean_neighbors": mean_k, "spacing_h": 0.5, "h": 0.007, "dt": 5e-5,
          "scene": "reference defaults E=1.5e5 nu=0.4 m=1e-4 x=-1, v0=(0,-0.4,0)", "mode": mode,

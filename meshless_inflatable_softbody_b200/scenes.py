@@ -54,6 +54,25 @@ def jittered_beam(n_target: int, h: float = 0.007, spacing: float = 0.5, jitter:
     return (g + np.asarray(centre, np.float64)).astype(np.float32)
 
 
+def jittered_ellipsoid(n_target: int, h: float = 0.007, spacing: float = 0.5, jitter: float = 0.2, seed: int = 0,
+                       aspect=(4.0, 1.0, 1.0), centre=(0.0, 0.07, 0.0), low_drop: bool = False):
+    """Jittered lattice clipped to an ellipsoid with semi-axes proportional to `aspect` (long axis x by default):
+    the slab-partitioned multi-GPU scene -- smooth surface like the sphere, long enough to cut into slabs."""
+    s = spacing * h
+    a = np.asarray(aspect, np.float64)
+    unit = (3.0 * n_target * s ** 3 / (4.0 * np.pi * a.prod())) ** (1.0 / 3.0)
+    semi = unit * a
+    axes = [np.arange(-int(np.ceil(r / s)) - 1, int(np.ceil(r / s)) + 2) * s for r in semi]
+    g = np.stack(np.meshgrid(*axes, indexing="ij"), -1).reshape(-1, 3)
+    rng = np.random.default_rng(seed)
+    g = g + rng.uniform(-jitter * s, jitter * s, size=g.shape)
+    g = g[((g / semi[None, :]) ** 2).sum(1) <= 1.0]
+    c = np.asarray(centre, np.float64).copy()
+    if low_drop:
+        c[1] = 0.0006 - g[:, 1].min()
+    return (g + c).astype(np.float32)
+
+
 def shell_mask(x0: np.ndarray, h: float, centre=None):
     """Particles within 2h of the surface of the (assumed spherical) cloud."""
     c = x0.mean(0) if centre is None else np.asarray(centre)

@@ -15,10 +15,11 @@ pytestmark = pytest.mark.gpu
 FLOOR_MULT = 4.0
 
 
-def _beam(n=5000):
-    x0 = scenes.jittered_beam(n, seed=0, aspect=(6.0, 1.0, 1.0), centre=(0.0, 0.012, 0.0))
-    x0[:, 1] += 0.0006 - x0[:, 1].min()           # low drop: ground contact within the run
-    return x0.astype(np.float32)
+def _beam(n=9000):
+    # elongated smooth body, low drop: ground contact within the run.  A flat-faced box and an ellipsoid thinner than
+    # ~3.5 h in its minor axes (aspect 5 at this size) diverge at the reference defaults -- in the oracle too -- so the
+    # partition tests use a 4:1:1 ellipsoid (minor radius 4.1 h, 17 cells along x: 3 slabs of >= 3 cells)
+    return scenes.jittered_ellipsoid(n, seed=0, aspect=(4.0, 1.0, 1.0), low_drop=True)
 
 
 @pytest.mark.parametrize("world", [2, 3])
@@ -26,7 +27,7 @@ def test_partitioned_run_matches_single_domain(world):
     from meshless_inflatable_softbody_b200 import Simulator
     cfg = SceneConfig()
     x0 = _beam()
-    steps = 60
+    steps = 80
     part = SlabPartition.build(x0, cfg.h, world)
     sims = [SlabSimulator(x0, cfg, rank=r, world_size=world, partition=part, in_process=True) for r in range(world)]
     for s in sims:
@@ -72,7 +73,7 @@ def _nccl_worker(rank, world, x0, steps, port, out_dir):
 def test_nccl_halo_exchange_two_gpus(tmp_path):
     import torch.multiprocessing as mp
     from meshless_inflatable_softbody_b200 import Simulator
-    x0 = _beam(8000)
+    x0 = _beam(12000)
     steps = 40
     mp.spawn(_nccl_worker, args=(2, x0, steps, 29731, str(tmp_path)), nprocs=2, join=True)
     X, V = np.load(tmp_path / "X.npy"), np.load(tmp_path / "V.npy")

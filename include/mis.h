@@ -171,6 +171,10 @@ int mis_sdf_destroy(MisSdf* sdf);
  * frame of `points` by forward differences of step fd_eps in model space (3 extra evaluations). */
 int mis_sdf_query(MisSdf* sdf, const float* points_dev, int n, const float* xform_host,
                   float* sdf_dev, float* grad_dev, float fd_eps, void* stream);
+/* Hidden-layer kernel choice (tests / tuning): 0 = automatic (split-K over 8-CTA clusters with a distributed-shared-memory
+ * reduction when the row count is small or lives on the device -- the per-step contact query; persistent 128 x 256 tiles for
+ * bulk queries), 1 = always split-K, 2 = always big tiles.  Both are correct for any row count.              */
+int mis_sdf_set_gemm_path(MisSdf* sdf, int path);
 /* kernels launched so far by this network / of which tcgen05 GEMM launches                    */
 long long mis_sdf_launch_count(MisSdf* sdf, long long* gemm_launches);
 /* Measurement aid: device milliseconds of `reps` back-to-back hidden-layer GEMMs (layer 1) on

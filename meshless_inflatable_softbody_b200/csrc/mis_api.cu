@@ -480,18 +480,21 @@ static void enqueue_contact(MisSim* s, const View& v, cudaStream_t st) {
     const int n = s->n;
     MisSdf* net = s->sdf;
     cudaMemsetAsync(s->con_count, 0, 3 * sizeof(int), st);
-    cudaMemsetAsync(s->fcon, 0, (size_t)n * sizeof(float4), st);
-    k_contact_select<<<nblk(n, 256), 256, 0, st>>>(v.xcur, n, s->sdf_xf, s->sdf_lo, s->sdf_hi, s->con_idx, s->con_count, s->con_pts);
+    k_contact_select<<<nblk(n, 256), 256, 0, st>>>(v.xcur, n, s->sdf_xf, s->sdf_lo, s->sdf_hi, s->con_idx, s->con_count, s->con_pts, s->fcon);
     const long long l0 = net->launches;
-    sdf_forward(net, s->con_pts, nullptr, n, s->con_count, s->sdf_xf, make_float3(0.f, 0.f, 0.f), net->vals, st);
-    k_contact_narrow<<<nblk(n, 256), 256, 0, st>>>(net->vals, s->con_idx, s->con_pts, s->con_count, s->p.col_range,
-                                                   s->con_idx2, s->con_pts2, s->con_s0, s->con_count + 1);
+    int fb = 0;
+    const int H = net->H;
+    sdf_forward(net, s->con_pts, nullptr, n, s->con_count, s->sdf_xf, make_float3(0.f, 0.f, 0.f), nullptr, st, 0, &fb);
+    launch_k(k_contact_last_narrow, dim3(148 * 2), dim3(256), 0, st, true,
+             (const float*)net->act[fb][0], (const float*)net->act[fb][1], n, (const int*)s->con_count, (const float*)net->wl, (const float*)net->bl, H, s->p.col_range,
+             (const int*)s->con_idx, (const float*)s->con_pts, s->con_idx2, s->con_pts2, s->con_s0, s->con_count + 1);
     // the three forward differences of the in-contact particles as ONE pass of 3 x count rows (row 3 r + axis);
     // the chain's capacity is n rows, so at most n / 3 particles can be in the band at once (far more than a surface holds)
     const float e = s->sdf_eps;
-    sdf_forward(net, s->con_pts2, nullptr, n, s->con_count + 2, s->sdf_xf, make_float3(e, 0.f, 0.f), net->vals + net->cap, st, 1);
-    k_contact_apply<<<nblk(n, 256), 256, 0, st>>>(s->con_s0, net->vals + net->cap, s->con_idx2, s->con_count + 1, n, 1.f / e, s->sdf_xf,
-                                                  s->p.col_range, s->p.k_col, s->fcon);
+    sdf_forward(net, s->con_pts2, nullptr, n, s->con_count + 2, s->sdf_xf, make_float3(e, 0.f, 0.f), nullptr, st, 1, &fb, true);
+    launch_k(k_contact_last_apply, dim3(148 * 2), dim3(256), 0, st, true,
+             (const float*)net->act[fb][0], (const float*)net->act[fb][1], n, (const int*)(s->con_count + 1), (const float*)net->wl, (const float*)net->bl, H,
+             (const float*)s->con_s0, (const int*)s->con_idx2, 1.f / e, s->sdf_xf, s->p.col_range, s->p.k_col, s->fcon);
     s->launches += 3 + (net->launches - l0);
 }
 
@@ -785,6 +788,13 @@ extern "C" int mis_sdf_query(MisSdf* s, const float* points_dev, int n, const fl
     return MIS_OK;
 }
 
+extern "C" int mis_sdf_set_gemm_path(MisSdf* s, int path) {
+    if (!s || path < 0 || path > 2) return fail(MIS_E_INVALID, "mis_sdf_set_gemm_path: path must be 0, 1 or 2");
+    if (path == 1 && s->H > SK_MAX_KBS * SK_SPLIT * SDF_BK) return fail(MIS_E_UNSUPPORTED, "split-K kernel supports hidden widths up to 1024");
+    s->force_path = path;
+    return MIS_OK;
+}
+
 extern "C" long long mis_sdf_launch_count(MisSdf* s, long long* gemm_launches) {
     if (!s) return 0;
     if (gemm_launches) *gemm_launches = s->gemm_launches;
@@ -797,17 +807,22 @@ extern "C" int mis_sdf_profile_gemm(MisSdf* s, int m, int reps, void* stream, do
     cudaStream_t st = (cudaStream_t)stream;
     CK(sdf_reserve(s, m));
     CK(cudaFuncSetAttribute(k_sdf_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_sdf_gemm_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES));
     const int m_pad = (m + 127) / 128 * 128;
     CK(cudaMemsetAsync(s->act[0][0], 0, (size_t)m_pad * s->H * sizeof(float), st));
     CK(cudaMemsetAsync(s->act[0][1], 0, (size_t)m_pad * s->H * sizeof(float), st));
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const bool skinny = s->force_path ? (s->force_path == 1) : (s->H <= SK_MAX_KBS * SK_SPLIT * SDF_BK && m <= 1024);
     const int tiles = (s->H / SDF_BN) * (m_pad / SDF_BM);
     const int grid = tiles < s->num_sms ? tiles : s->num_sms;
-    k_sdf_gemm<<<grid, SDF_THREADS, SDF_SMEM_BYTES, st>>>(s->act[0][0], s->act[0][1], s->Whi[0], s->Wlo[0], s->bh[0], s->H, s->H, s->act[1][0], s->act[1][1], m_pad, nullptr);
+    auto one = [&]() {
+        if (skinny) k_sdf_gemm_sk<<<(s->H / SK_BN) * SK_SPLIT, SDF_THREADS, SK_SMEM_BYTES, st>>>(s->act[0][0], s->act[0][1], s->Whi[0], s->Wlo[0], s->bh[0], s->H, s->H, s->act[1][0], s->act[1][1], m, nullptr);
+        else k_sdf_gemm<<<grid, SDF_THREADS, SDF_SMEM_BYTES, st>>>(s->act[0][0], s->act[0][1], s->Whi[0], s->Wlo[0], s->bh[0], s->H, s->H, s->act[1][0], s->act[1][1], m_pad, nullptr);
+    };
+    one();
     CK(cudaEventRecord(e0, st));
-    for (int r = 0; r < reps; r++)
-        k_sdf_gemm<<<grid, SDF_THREADS, SDF_SMEM_BYTES, st>>>(s->act[0][0], s->act[0][1], s->Whi[0], s->Wlo[0], s->bh[0], s->H, s->H, s->act[1][0], s->act[1][1], m_pad, nullptr);
+    for (int r = 0; r < reps; r++) one();
     CK(cudaEventRecord(e1, st));
     CK(cudaStreamSynchronize(st));
     float ms = 0.f;

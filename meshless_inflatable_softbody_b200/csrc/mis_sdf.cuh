@@ -38,6 +38,12 @@ __host__ __device__ __forceinline__ size_t sdf_tile_off(int r, int k, int KB) {
     return ((size_t)(r >> 7) * KB + (k >> 5)) * SDF_TILE_FLOATS + ((r & 127) >> 3) * 256 + ((k & 31) >> 2) * 32 + (r & 7) * 4 + (k & 3);
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may start while its
+// predecessor in the stream still runs; pdl_wait() blocks until the predecessor has completed and its writes are visible (a no-op
+// for a normally launched kernel), pdl_trigger() lets the successor's blocks be scheduled early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -254,6 +260,234 @@ __global__ void __launch_bounds__(SDF_THREADS, 1) k_sdf_gemm(const float* __rest
     }
 }
 
+// ---------------------------------------------------------------- the hidden layer for FEW rows (per-step contact queries)
+// With a few hundred live rows the layer is bound by how fast the 8 MB of W (hi + lo planes) and the activations reach the SMs and by
+// fixed latencies, not by the tensor pipe: one 128 x 256 tile per CTA would leave 144 SMs idle and make 4 SMs ingest 3 MB each.
+// k_sdf_gemm_sk spreads one layer over (N / 64) clusters x 8 CTAs: cluster c owns output columns [64 c, 64 c + 64); CTA rank r of the
+// cluster owns the K slice [K r / 8, K (r + 1) / 8) (split-K), i.e. 64 KB of W and 128 KB of activations per 128-row block.  The 8
+// partial accumulators (TMEM -> shared memory) are reduced through distributed shared memory in FIXED rank order (deterministic): rank r
+// finishes columns [8 r, 8 r + 8) of the tile (+ bias, ReLU, hi/lo split, stores into the next layer's UMMA tiles).
+// Shared memory is kept under half an SM (2 x 48 KB stages; the fp32 partial tile aliases stage 0) and only 64 TMEM columns are
+// allocated, so two CTAs fit on an SM: at most 15 clusters of 8 one-CTA-per-SM blocks are co-resident on a B200 (measured), and the
+// 16 column tiles of a 1024-wide layer must not fall into two waves.  Row-blocks are processed one after the other (any row count is
+// correct; the bulk kernel above is the efficient one for many rows).
+constexpr int SK_BN = 64, SK_SPLIT = 8, SK_STAGES = 2;
+constexpr int SK_W_HALF_BYTES = SK_BN * SDF_BK * 4;                        // 64 rows x 32 k of one plane = 8 KB
+constexpr int SK_MAX_KBS = 64;                                             // k-blocks per rank (W is streamed with A, so only a sanity bound)
+constexpr int SK_STAGE_BYTES = 2 * SDF_TILE_BYTES + 2 * SK_W_HALF_BYTES;   // A_hi, A_lo, W_hi, W_lo of one k-block: 48 KB
+constexpr int SK_STAGING_BYTES = SDF_BM * SK_BN * 4;                       // 32 KB fp32 partial tile (aliases the A part of stage 0)
+constexpr int SK_TMEM_COLS = 64;
+constexpr int SK_SMEM_BYTES = SK_STAGES * SK_STAGE_BYTES + 256 + 1024;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+    uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cluster_addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(cluster_addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_smem_f4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+#ifdef MIS_SK_TIMING
+__device__ unsigned long long sk_dbg[64];
+__device__ unsigned long long sk_cta[4 * 256];
+__device__ __forceinline__ unsigned long long sk_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define SK_T(slot) do { if (blockIdx.x == MIS_SK_TIMING) sk_dbg[slot] = sk_now(); } while (0)
+#define SK_CTA(k) do { if (threadIdx.x == 0) { sk_cta[4 * blockIdx.x + (k)] = sk_now(); if ((k) == 0) { unsigned sm_; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_)); sk_cta[4 * blockIdx.x + 2] = sm_; } } } while (0)
+#else
+#define SK_T(slot) do { } while (0)
+#define SK_CTA(k) do { } while (0)
+#endif
+
+__global__ void __cluster_dims__(SK_SPLIT, 1, 1) __launch_bounds__(SDF_THREADS, 2)
+k_sdf_gemm_sk(const float* __restrict__ Xhi, const float* __restrict__ Xlo, const float* __restrict__ Whi, const float* __restrict__ Wlo,
+              const float* __restrict__ bias, int K, int N, float* __restrict__ Yhi, float* __restrict__ Ylo,
+              int m_rows, const int* __restrict__ m_count) {
+    extern __shared__ uint8_t smem_raw[];
+    if (threadIdx.x == 0) SK_T(0);
+    SK_CTA(0);
+    pdl_trigger();                                             // the next layer may set itself up while this one runs
+    const int nb = blockIdx.x / SK_SPLIT;                      // cluster id = column tile
+    if (nb >= N / SK_BN) return;                               // uniform per cluster
+    const uint32_t rank = cluster_ctarank();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KB = K / SDF_BK;
+    const int kbs = KB / SK_SPLIT;                             // k-blocks of this rank (<= SK_MAX_KBS)
+    const int k0 = (int)rank * kbs;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t stg_sm = base;                              // partial tile: the A part of stage 0, free once the row-block's MMAs retired
+    const uint32_t bars = base + SK_STAGES * SK_STAGE_BYTES;
+    // full[s] +8 s | empty[s] +16 + 8 s | tfull +32 | stg_done +40 | ready +48 | freeb +56 | tmem pointer +64
+    const uint32_t BAR_F = bars, BAR_E = bars + 16, BAR_TF = bars + 32, BAR_SD = bars + 40, BAR_RDY = bars + 48, BAR_FREE = bars + 56,
+                   TMEM_SLOT = bars + 64;
+    volatile uint32_t* tmem_ptr_sm = reinterpret_cast<volatile uint32_t*>(smem_raw + (TMEM_SLOT - smem_u32(smem_raw)));
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(SK_BN >> 3) << 17) | ((uint32_t)(SDF_BM >> 4) << 24);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SK_STAGES; s++) { mbar_init(BAR_F + 8 * s, 1); mbar_init(BAR_E + 8 * s, 1); }
+        mbar_init(BAR_TF, 1); mbar_init(BAR_SD, 4);
+        mbar_init(BAR_RDY, SK_SPLIT); mbar_init(BAR_FREE, SK_SPLIT);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(TMEM_SLOT), "r"((uint32_t)SK_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    // the peers' barriers must be initialised before anyone arrives on them remotely
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = *tmem_ptr_sm;
+    if (threadIdx.x == 0) SK_T(1);
+    // everything above is independent of the previous kernel; its outputs (activations, the device-side row count) are read below
+    pdl_wait();
+    const int live = m_count ? min(*m_count, m_rows) : m_rows;
+    const int row_blocks = (live + SDF_BM - 1) / SDF_BM;       // uniform over the grid; 0: nothing to do but release TMEM
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // W slice: rows [64 nb, 64 nb + 64) = half a 128-row tile (8 KB contiguous per k-block and plane), k-blocks [k0, k0 + kbs)
+            const int n0 = nb * SK_BN;
+            const size_t wrow = (size_t)(n0 >> 7) * KB * SDF_TILE_FLOATS + (size_t)((n0 & 127) >> 3) * 256;
+            uint32_t it = 0;
+            for (int mb = 0; mb < row_blocks; mb++) {
+                if (mb > 0) mbar_wait(BAR_SD, (uint32_t)(mb - 1) & 1);          // the previous partial tile (aliasing stage 0) has been consumed
+                for (int kb = 0; kb < kbs; kb++, it++) {
+                    const uint32_t s = it % SK_STAGES, ph = (it / SK_STAGES) & 1;
+                    mbar_wait(BAR_E + 8 * s, ph ^ 1);
+                    const uint32_t full = BAR_F + 8 * s;
+                    mbar_expect_tx(full, SK_STAGE_BYTES);
+                    const uint32_t st = base + s * SK_STAGE_BYTES;
+                    const size_t oa = ((size_t)mb * KB + k0 + kb) * SDF_TILE_FLOATS;
+                    const size_t ow = wrow + (size_t)(k0 + kb) * SDF_TILE_FLOATS;
+                    tma_bulk_g2s(st, Xhi + oa, SDF_TILE_BYTES, full);
+                    tma_bulk_g2s(st + SDF_TILE_BYTES, Xlo + oa, SDF_TILE_BYTES, full);
+                    tma_bulk_g2s(st + 2 * SDF_TILE_BYTES, Whi + ow, SK_W_HALF_BYTES, full);
+                    tma_bulk_g2s(st + 2 * SDF_TILE_BYTES + SK_W_HALF_BYTES, Wlo + ow, SK_W_HALF_BYTES, full);
+                }
+                if (mb == 0) SK_T(3);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int mb = 0; mb < row_blocks; mb++) {
+                // the accumulator is free: the loads of this row-block were only issued after the previous epilogue finished (BAR_SD)
+                for (int kb = 0; kb < kbs; kb++, it++) {
+                    const uint32_t s = it % SK_STAGES, ph = (it / SK_STAGES) & 1;
+                    mbar_wait(BAR_F + 8 * s, ph);
+                    if (it == 0) SK_T(5);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t as = base + s * SK_STAGE_BYTES, ws = as + 2 * SDF_TILE_BYTES;
+#pragma unroll
+                    for (int ks = 0; ks < SDF_BK / 8; ks++) {
+                        const uint32_t ko = ks * 256;
+                        const uint64_t ahi = umma_desc(as + ko), alo = umma_desc(as + SDF_TILE_BYTES + ko);
+                        const uint64_t bhi = umma_desc(ws + ko), blo = umma_desc(ws + SK_W_HALF_BYTES + ko);
+                        umma_tf32(tmem_acc, alo, bhi, idesc, (kb | ks) ? 1u : 0u);
+                        umma_tf32(tmem_acc, ahi, blo, idesc, 1u);
+                        umma_tf32(tmem_acc, ahi, bhi, idesc, 1u);
+                    }
+                    umma_commit(BAR_E + 8 * s);
+                }
+                umma_commit(BAR_TF);
+                if (mb == 0) SK_T(6);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int rl = 32 * q + lane;                               // row inside the 128-row block = TMEM lane
+        const int et = threadIdx.x - 64;                            // 0..127 among the epilogue threads
+        const int KBn = N / SDF_BK;
+        const size_t row_off = (size_t)(rl >> 3) * 256 + (rl & 7) * 4;
+        const int col0 = nb * SK_BN + 8 * (int)rank;                // the 8 output columns this CTA finishes
+        const float4 bia0 = __ldg(reinterpret_cast<const float4*>(bias + col0));
+        const float4 bia1 = __ldg(reinterpret_cast<const float4*>(bias + col0 + 4));
+        const size_t out_off = (size_t)(col0 / SDF_BK) * SDF_TILE_FLOATS + (size_t)((col0 % SDF_BK) / 4) * 32 + row_off;
+        for (int mb = 0; mb < row_blocks; mb++) {
+            const uint32_t par = (uint32_t)mb & 1;
+            mbar_wait(BAR_TF, par);                                 // every MMA of this row-block has retired: TMEM complete, stage 0 idle
+            if (et == 0 && mb == 0) SK_T(7);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c = 0; c < SK_BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)c, v);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; c4++)                      // staging[c / 4][row][4]: consecutive lanes -> consecutive 16-byte words
+                    st_smem_f4(stg_sm + (uint32_t)(((c >> 2) + c4) * SDF_BM + rl) * 16u, __uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]),
+                               __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
+            }
+            if (et == 0 && mb == 0) SK_T(9);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("fence.acq_rel.cluster;" ::: "memory");
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0 && mb == 0) SK_T(10);
+            if (et < SK_SPLIT) mbar_arrive_remote(mapa_u32(BAR_RDY, (uint32_t)et));
+            mbar_wait_cluster(BAR_RDY, par);                        // all 8 partial tiles are in shared memory
+            if (et == 0 && mb == 0) SK_T(11);
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (uint32_t r = 0; r < SK_SPLIT; r++) {               // fixed order: deterministic
+                const uint32_t ra = mapa_u32(stg_sm + (uint32_t)((2 * rank) * SDF_BM + rl) * 16u, r);
+                const float4 a0 = ld_dsmem_f4(ra), a1 = ld_dsmem_f4(ra + SDF_BM * 16u);
+                acc[0] += a0.x; acc[1] += a0.y; acc[2] += a0.z; acc[3] += a0.w;
+                acc[4] += a1.x; acc[5] += a1.y; acc[6] += a1.z; acc[7] += a1.w;
+            }
+            if (et == 0 && mb == 0) SK_T(12);
+            asm volatile("bar.sync 1, 128;" ::: "memory");          // all reads of the peers' tiles are done
+            if (et < SK_SPLIT) mbar_arrive_remote(mapa_u32(BAR_FREE, (uint32_t)et));
+            const float bv[8] = {bia0.x, bia0.y, bia0.z, bia0.w, bia1.x, bia1.y, bia1.z, bia1.w};
+            float h[8], l[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const float y = fmaxf(acc[e] + bv[e], 0.f);
+                h[e] = tf32_hi(y); l[e] = y - h[e];
+            }
+            float* dh = Yhi + (size_t)mb * KBn * SDF_TILE_FLOATS + out_off;
+            float* dl = Ylo + (size_t)mb * KBn * SDF_TILE_FLOATS + out_off;
+            *reinterpret_cast<float4*>(dh) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(dh + 32) = make_float4(h[4], h[5], h[6], h[7]);
+            *reinterpret_cast<float4*>(dl) = make_float4(l[0], l[1], l[2], l[3]);
+            *reinterpret_cast<float4*>(dl + 32) = make_float4(l[4], l[5], l[6], l[7]);
+            if (et == 0 && mb == 0) SK_T(13);
+            mbar_wait_cluster(BAR_FREE, par);                       // no peer still reads this CTA's partial tile
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy accesses to the tile before the next TMA write
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR_SD);                     // stage 0 and the accumulator may be reused
+        }
+        if (et == 0) SK_T(14);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)SK_TMEM_COLS) : "memory");
+    }
+    if (threadIdx.x == 0) SK_T(15);
+    SK_CTA(1);
+}
+
 // ---------------------------------------------------------------- weights
 // weight_norm (deepsdf.py:3): W[o, :] = g[o] * v[o, :] / ||v[o, :]||.  One block per output row; writes the
 // plain fp32 row (first / last layer) and/or the hi / lo UMMA tiles (hidden layers).
@@ -298,6 +532,8 @@ __global__ void __launch_bounds__(256) k_sdf_layer0(const float* __restrict__ pt
                                                     const float* __restrict__ W0 /* [H,3] */, const float* __restrict__ b0, int H,
                                                     float* __restrict__ Yhi, float* __restrict__ Ylo) {
     const int chunks = H / 4;
+    pdl_trigger();
+    pdl_wait();
     const int live = m_count ? min(*m_count, m) : m;
     const long long work = (long long)((live + 127) & ~127) * chunks;        // whole row-blocks: the GEMM reads 128-row tiles
     for (long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x; gid < work; gid += (long long)gridDim.x * blockDim.x) {
@@ -331,13 +567,10 @@ __global__ void __launch_bounds__(256) k_sdf_layer0(const float* __restrict__ pt
 }
 
 // ---------------------------------------------------------------- last layer: Linear(H, 1) on CUDA cores
-// One warp per row; lane = k-block, fixed summation order (deterministic).
-__global__ void __launch_bounds__(256) k_sdf_last(const float* __restrict__ Xhi, const float* __restrict__ Xlo, int m, const int* __restrict__ m_count,
-                                                  const float* __restrict__ w /* [H] */, const float* __restrict__ b, int H, float* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const int live = m_count ? min(*m_count, m) : m;
+// One warp per row; lane = k-block, fixed summation order (deterministic).  Returns the full dot product in every lane.
+__device__ __forceinline__ float sdf_last_row(const float* __restrict__ Xhi, const float* __restrict__ Xlo, int r,
+                                              const float* __restrict__ w, int H, int lane) {
     const int KB = H / SDF_BK;
-    for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < live; r += gridDim.x * 8) {
     float acc = 0.f;
     for (int kb = lane; kb < KB; kb += 32) {
         const size_t base = ((size_t)(r >> 7) * KB + kb) * SDF_TILE_FLOATS + ((r & 127) >> 3) * 256 + (r & 7) * 4;
@@ -352,7 +585,17 @@ __global__ void __launch_bounds__(256) k_sdf_last(const float* __restrict__ Xhi,
     }
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
-    if (lane == 0) out[r] = acc + b[0];
+    return acc;
+}
+
+__global__ void __launch_bounds__(256) k_sdf_last(const float* __restrict__ Xhi, const float* __restrict__ Xlo, int m, const int* __restrict__ m_count,
+                                                  const float* __restrict__ w /* [H] */, const float* __restrict__ b, int H, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    pdl_wait();
+    const int live = m_count ? min(*m_count, m) : m;
+    for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < live; r += gridDim.x * 8) {
+        const float acc = sdf_last_row(Xhi, Xlo, r, w, H, lane);
+        if (lane == 0) out[r] = acc + b[0];
     }
 }
 

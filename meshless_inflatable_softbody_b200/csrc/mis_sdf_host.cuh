@@ -17,9 +17,22 @@ struct MisSdf {
     long long launches = 0;
     long long gemm_launches = 0;
     int num_sms = 148;         // persistent GEMM grid: one CTA per SM
+    int force_path = 0;        // tests / tuning: 0 = automatic, 1 = split-K cluster kernel, 2 = persistent big-tile kernel
 };
 
 namespace mis {
+
+// kernel launch, optionally as a programmatic dependent launch of the previous kernel in the stream (see pdl_wait / pdl_trigger)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 inline void sdf_free(MisSdf* s) {
     if (!s) return;
@@ -50,11 +63,15 @@ inline cudaError_t sdf_reserve(MisSdf* s, int rows) {
 
 // One forward pass of the chain for `rows` points (rows <= cap): points -> out[rows].
 //   pts/idx: point r is pts[idx ? idx[r] : r]; xf/shift: p_model = A (p - t) + shift; m_count: optional device-side live-row count.
+// Returns (through *final_buf) the index of the activation buffer holding the last hidden layer's output when out == nullptr
+// (the caller runs its own fused last-layer kernel).
+// pdl_first: layer 0 is a programmatic dependent launch of the caller's previous kernel (which must call pdl_trigger / exit).
 inline cudaError_t sdf_forward(MisSdf* s, const float* pts, const int* idx, int rows, const int* m_count, const SdfXform& xf, float3 shift,
-                               float* out, cudaStream_t st, int fd3 = 0) {
+                               float* out, cudaStream_t st, int fd3 = 0, int* final_buf = nullptr, bool pdl_first = false) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_sdf_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sdf_gemm_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -62,19 +79,37 @@ inline cudaError_t sdf_forward(MisSdf* s, const float* pts, const int* idx, int 
     const int H = s->H;
     const long long threads0 = (long long)m_pad * (H / 4);
     const long long blocks0 = (threads0 + 255) / 256;
-    k_sdf_layer0<<<(unsigned)(blocks0 < 148 * 16 ? blocks0 : 148 * 16), 256, 0, st>>>(pts, idx, rows, m_pad, m_count, xf, shift, fd3, s->W0, s->b0, H, s->act[0][0], s->act[0][1]);
+    const long long cap0 = m_count ? 148 * 4 : 148 * 16;            // device-side counts are small: a short grid lets the next kernel start early
+    cudaError_t le = launch_k(k_sdf_layer0, dim3((unsigned)(blocks0 < cap0 ? blocks0 : cap0)), dim3(256), 0, st, pdl_first,
+                              pts, idx, rows, m_pad, m_count, xf, shift, fd3, (const float*)s->W0, (const float*)s->b0, H, s->act[0][0], s->act[0][1]);
+    if (le != cudaSuccess) return le;
     s->launches++;
+    // few rows (a device-side count = the per-step contact query, or a small host-side count): split-K over 8-CTA clusters;
+    // bulk queries: persistent 128 x 256 tiles
+    const bool skinny = s->force_path ? (s->force_path == 1) : (H <= SK_MAX_KBS * SK_SPLIT * SDF_BK && (m_count != nullptr || rows <= 1024));
     int cur = 0;
     for (size_t l = 0; l < s->Whi.size(); l++) {
-        const int tiles = (H / SDF_BN) * (m_pad / SDF_BM);
-        k_sdf_gemm<<<tiles < s->num_sms ? tiles : s->num_sms, SDF_THREADS, SDF_SMEM_BYTES, st>>>(
-            s->act[cur][0], s->act[cur][1], s->Whi[l], s->Wlo[l], s->bh[l], H, H, s->act[cur ^ 1][0], s->act[cur ^ 1][1], rows, m_count);
+        if (skinny) {
+            le = launch_k(k_sdf_gemm_sk, dim3((H / SK_BN) * SK_SPLIT), dim3(SDF_THREADS), SK_SMEM_BYTES, st, true,
+                          (const float*)s->act[cur][0], (const float*)s->act[cur][1], (const float*)s->Whi[l], (const float*)s->Wlo[l], (const float*)s->bh[l],
+                          H, H, s->act[cur ^ 1][0], s->act[cur ^ 1][1], rows, m_count);
+            if (le != cudaSuccess) return le;
+        } else {
+            const int tiles = (H / SDF_BN) * (m_pad / SDF_BM);
+            k_sdf_gemm<<<tiles < s->num_sms ? tiles : s->num_sms, SDF_THREADS, SDF_SMEM_BYTES, st>>>(
+                s->act[cur][0], s->act[cur][1], s->Whi[l], s->Wlo[l], s->bh[l], H, H, s->act[cur ^ 1][0], s->act[cur ^ 1][1], rows, m_count);
+        }
         s->launches++; s->gemm_launches++;
         cur ^= 1;
     }
-    const int blocksl = (rows + 7) / 8;
-    k_sdf_last<<<blocksl < 148 * 8 ? blocksl : 148 * 8, 256, 0, st>>>(s->act[cur][0], s->act[cur][1], rows, m_count, s->wl, s->bl, H, out);
-    s->launches++;
+    if (final_buf) *final_buf = cur;
+    if (out) {
+        const int blocksl = (rows + 7) / 8;
+        le = launch_k(k_sdf_last, dim3(blocksl < 148 * 8 ? blocksl : 148 * 8), dim3(256), 0, st, skinny,
+                      (const float*)s->act[cur][0], (const float*)s->act[cur][1], rows, m_count, (const float*)s->wl, (const float*)s->bl, H, out);
+        if (le != cudaSuccess) return le;
+        s->launches++;
+    }
     return cudaGetLastError();
 }
 
@@ -93,11 +128,13 @@ __global__ void __launch_bounds__(256) k_sdf_fd_grad(const float* __restrict__ v
 // ---------------------------------------------------------------- per-step contact (extension of sim.py:238-244)
 // broad phase: cell-sorted particles whose model-space position lies in the obstacle's bounding box (+ margin)
 __global__ void __launch_bounds__(256) k_contact_select(const float4* __restrict__ xcur, int n, SdfXform xf, float3 lo, float3 hi,
-                                                        int* __restrict__ idx, int* __restrict__ count, float* __restrict__ pts_out) {
+                                                        int* __restrict__ idx, int* __restrict__ count, float* __restrict__ pts_out,
+                                                        float4* __restrict__ fcon) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     bool in = false;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
     if (s < n) {
+        fcon[s] = make_float4(0.f, 0.f, 0.f, 0.f);        // particles outside the contact band feel no obstacle force
         p = xcur[s];
         const float px = p.x - xf.t[0], py = p.y - xf.t[1], pz = p.z - xf.t[2];
         const float x = xf.A[0] * px + xf.A[1] * py + xf.A[2] * pz;
@@ -119,43 +156,56 @@ __global__ void __launch_bounds__(256) k_contact_select(const float4* __restrict
     }
 }
 
-// narrow phase: keep the candidates whose value is inside the contact band (sdf < range); only they need a normal
-__global__ void __launch_bounds__(256) k_contact_narrow(const float* __restrict__ vals, const int* __restrict__ idx, const float* __restrict__ pts,
-                                                        const int* __restrict__ count, float range,
-                                                        int* __restrict__ idx2, float* __restrict__ pts2, float* __restrict__ s0c, int* __restrict__ count2) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool in = r < *count && vals[r] < range;
-    const unsigned m = __ballot_sync(0xffffffffu, in);
-    if (m == 0) return;
+// last layer of the value pass fused with the narrow phase: one warp per candidate row finishes sdf(p) (Linear(H,1)) and keeps
+// the candidates inside the contact band (sdf < range); only they need a normal.  The order of the kept list depends on the
+// atomics, the per-particle results do not (rows of the chain are independent).
+__global__ void __launch_bounds__(256) k_contact_last_narrow(const float* __restrict__ Xhi, const float* __restrict__ Xlo, int m, const int* __restrict__ count,
+                                                             const float* __restrict__ w, const float* __restrict__ b, int H, float range,
+                                                             const int* __restrict__ idx, const float* __restrict__ pts,
+                                                             int* __restrict__ idx2, float* __restrict__ pts2, float* __restrict__ s0c, int* __restrict__ count2) {
     const int lane = threadIdx.x & 31;
-    int basep = 0;
-    if (lane == __ffs(m) - 1) { basep = atomicAdd(count2, __popc(m)); atomicAdd(count2 + 1, 3 * __popc(m)); }   // [1] = rows of the FD pass
-    basep = __shfl_sync(0xffffffffu, basep, __ffs(m) - 1);
-    if (in) {
-        const int q = basep + __popc(m & ((1u << lane) - 1));
-        idx2[q] = idx[r];
-        pts2[3 * (size_t)q] = pts[3 * (size_t)r]; pts2[3 * (size_t)q + 1] = pts[3 * (size_t)r + 1]; pts2[3 * (size_t)q + 2] = pts[3 * (size_t)r + 2];
-        s0c[q] = vals[r];
+    pdl_trigger();
+    pdl_wait();
+    const int live = min(*count, m);
+    for (int r = blockIdx.x * 8 + (threadIdx.x >> 5); r < live; r += gridDim.x * 8) {
+        const float v = sdf_last_row(Xhi, Xlo, r, w, H, lane) + b[0];
+        if (lane == 0 && v < range) {
+            const int q = atomicAdd(count2, 1);
+            atomicAdd(count2 + 1, 3);                                   // [1] = rows of the forward-difference pass
+            idx2[q] = idx[r];
+            pts2[3 * (size_t)q] = pts[3 * (size_t)r]; pts2[3 * (size_t)q + 1] = pts[3 * (size_t)r + 1]; pts2[3 * (size_t)q + 2] = pts[3 * (size_t)r + 2];
+            s0c[q] = v;
+        }
     }
 }
 
-// contact law: delta = range - sdf(p_model); f = delta^2 k n, n = grad / |grad| in world space.
-// fd holds the three forward-difference evaluations of the in-contact particles, interleaved (3 r + axis).
-__global__ void __launch_bounds__(256) k_contact_apply(const float* __restrict__ s0c, const float* __restrict__ fd, const int* __restrict__ idx2,
-                                                       const int* __restrict__ count2, int fd_rows, float inv_eps, SdfXform xf, float range, float k_col,
-                                                       float4* __restrict__ fcon) {
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= *count2 || 3 * r + 2 >= fd_rows) return;      // fd_rows = rows the FD pass could evaluate
-    const float s0 = s0c[r];
-    const float gx = (fd[3 * (size_t)r] - s0) * inv_eps, gy = (fd[3 * (size_t)r + 1] - s0) * inv_eps, gz = (fd[3 * (size_t)r + 2] - s0) * inv_eps;
-    float wx = xf.A[0] * gx + xf.A[3] * gy + xf.A[6] * gz;
-    float wy = xf.A[1] * gx + xf.A[4] * gy + xf.A[7] * gz;
-    float wz = xf.A[2] * gx + xf.A[5] * gy + xf.A[8] * gz;
-    const float nn = sqrtf(wx * wx + wy * wy + wz * wz);
-    if (!(nn > 1e-20f)) return;
-    const float d = range - s0;
-    const float f = d * d * k_col / nn;
-    fcon[idx2[r]] = make_float4(f * wx, f * wy, f * wz, 0.f);
+// last layer of the forward-difference pass (rows 3 q + axis) fused with the contact law:
+// delta = range - sdf(p_model); f = delta^2 k n, n = grad / |grad| in world space.  One warp per in-contact particle.
+__global__ void __launch_bounds__(256) k_contact_last_apply(const float* __restrict__ Xhi, const float* __restrict__ Xlo, int fd_rows, const int* __restrict__ count2,
+                                                            const float* __restrict__ w, const float* __restrict__ b, int H,
+                                                            const float* __restrict__ s0c, const int* __restrict__ idx2, float inv_eps, SdfXform xf,
+                                                            float range, float k_col, float4* __restrict__ fcon) {
+    const int lane = threadIdx.x & 31;
+    pdl_wait();
+    const int live = min(*count2, fd_rows / 3);                         // fd_rows = rows the FD pass could evaluate
+    for (int q = blockIdx.x * 8 + (threadIdx.x >> 5); q < live; q += gridDim.x * 8) {
+        const float sx = sdf_last_row(Xhi, Xlo, 3 * q, w, H, lane) + b[0];
+        const float sy = sdf_last_row(Xhi, Xlo, 3 * q + 1, w, H, lane) + b[0];
+        const float sz = sdf_last_row(Xhi, Xlo, 3 * q + 2, w, H, lane) + b[0];
+        if (lane == 0) {
+            const float s0 = s0c[q];
+            const float gx = (sx - s0) * inv_eps, gy = (sy - s0) * inv_eps, gz = (sz - s0) * inv_eps;
+            const float wx = xf.A[0] * gx + xf.A[3] * gy + xf.A[6] * gz;
+            const float wy = xf.A[1] * gx + xf.A[4] * gy + xf.A[7] * gz;
+            const float wz = xf.A[2] * gx + xf.A[5] * gy + xf.A[8] * gz;
+            const float nn = sqrtf(wx * wx + wy * wy + wz * wz);
+            if (nn > 1e-20f) {
+                const float d = range - s0;
+                const float f = d * d * k_col / nn;
+                fcon[idx2[q]] = make_float4(f * wx, f * wy, f * wz, 0.f);
+            }
+        }
+    }
 }
 
 }  // namespace mis

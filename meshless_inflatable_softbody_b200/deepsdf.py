@@ -100,6 +100,10 @@ class DeepSDF:
         x[:out_num] = torch.clamp(x[:out_num], min=1.0)
         return x
 
+    def set_gemm_path(self, path: int) -> None:
+        """0 = automatic, 1 = split-K cluster kernel (few rows), 2 = persistent big-tile kernel (bulk)."""
+        native.check(self.L.mis_sdf_set_gemm_path(self._h, int(path)), "mis_sdf_set_gemm_path")
+
     def profile_gemm(self, m: int, reps: int = 10) -> float:
         """Device milliseconds per hidden-layer GEMM launch on m rows (CUDA events)."""
         ms = C.c_double(0)

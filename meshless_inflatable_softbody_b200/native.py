@@ -105,6 +105,7 @@ SYMBOLS = {
                                  C.POINTER(C.c_void_p), _vp, C.POINTER(C.c_void_p)]),
     "mis_sdf_destroy": (C.c_int, [_vp]),
     "mis_sdf_query": (C.c_int, [_vp, _fp, C.c_int, C.POINTER(C.c_float), _fp, _fp, C.c_float, _vp]),
+    "mis_sdf_set_gemm_path": (C.c_int, [_vp, C.c_int]),
     "mis_sdf_launch_count": (C.c_longlong, [_vp, C.POINTER(C.c_longlong)]),
     "mis_sdf_profile_gemm": (C.c_int, [_vp, C.c_int, C.c_int, _vp, C.POINTER(C.c_double)]),
     "mis_set_sdf_contact": (C.c_int, [_vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, _vp]),

@@ -50,6 +50,26 @@ def test_ragged_sizes_against_oracle(seeded, n):
     assert np.abs(got[sub] - want).max() <= 4e-6 * np.abs(want).max() + 1e-7
 
 
+@pytest.mark.parametrize("path,n", [(1, 1), (1, 129), (1, 1000), (1, 1024 + 77), (1, 3000), (2, 1), (2, 129), (2, 1000)])
+def test_both_hidden_layer_kernels_at_any_row_count(seeded, path, n):
+    """The split-K cluster kernel (few rows: per-step contact) and the persistent big-tile kernel (bulk) are both correct for
+    any row count; 3000 rows = 24 row-blocks = 3 TMEM groups of the split-K kernel."""
+    st, net = seeded
+    rng = np.random.default_rng(100 + n)
+    p = rng.uniform(-1.0, 1.0, size=(n, 3)).astype(np.float32)
+    net.set_gemm_path(path)
+    try:
+        got = net(p).cpu().numpy()[:, 0]
+        again = net(p).cpu().numpy()[:, 0]
+    finally:
+        net.set_gemm_path(0)
+    sub = np.unique(np.concatenate([np.arange(min(n, 64)), np.arange(max(0, n - 64), n), rng.integers(0, n, 128)]))
+    want = do.forward(st, p[sub], np.float64)[:, 0]
+    assert np.isfinite(got).all()
+    assert np.abs(got[sub] - want).max() <= 4e-6 * np.abs(want).max() + 1e-7
+    assert np.array_equal(got, again)                       # fixed reduction order: bit-reproducible
+
+
 def test_small_network_and_octahedron_exactness():
     st = do.octahedron_state(0.03, hidden=256, n_linear=4)
     net = _net(st)

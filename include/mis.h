@@ -128,6 +128,13 @@ int mis_step(MisSim* sim, int n_steps, void* stream);
 /* position[f], velocity[f] of the current frame (sim.py:334,368-369), caller order.  */
 int mis_get_state(MisSim* sim, float* x_dev, float* v_dev, void* stream);
 int mis_get_state_host(MisSim* sim, float* x_host, float* v_host, void* stream);
+/* Streaming export for per-frame consumers (visualize every 50th frame sim.py:393-395, targets sim.py:363-369): the un-permute
+ * runs on `stream`, the device->host copies on a library-owned copy stream, so the following steps overlap the transfer.
+ * Up to two exports may be in flight (double-buffered staging); x_host / v_host (pinned) are valid once
+ * mis_wait_state_host(sim, pending_allowed) returns: it blocks until at most pending_allowed (0 or 1) exports are pending.
+ * mis_set_ext_force_host uploads through the same copy stream.                                        */
+int mis_get_state_host_async(MisSim* sim, float* x_host, float* v_host, void* stream);
+int mis_wait_state_host(MisSim* sim, int pending_allowed);
 /* Halo plumbing for slab-partitioned scenes (no reference counterpart: the reference is single-GPU).
  * part_1 of the NEXT step is fused into the force kernel, so after mis_step the positions of frame f+1
  * already exist; these two calls read / overwrite them for a subset of particles (caller ids, int32):

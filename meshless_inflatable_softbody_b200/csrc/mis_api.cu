@@ -86,7 +86,27 @@ struct MisSim {
     int* con_count = nullptr;                 // [0] broad-phase candidates, [1] particles in the contact band
     float *con_pts = nullptr, *con_pts2 = nullptr, *con_s0 = nullptr;
     float4* fcon = nullptr;
+    // host <-> device streaming on a second stream (copy engines overlap the step kernels): double-buffered staging
+    cudaStream_t copy_stream = nullptr;         // device -> host
+    cudaStream_t up_stream = nullptr;           // host -> device (separate, so an upload never queues behind a download that waits for a step)
+    cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_up_used[2] = {nullptr, nullptr}, ev_exp[2] = {nullptr, nullptr}, ev_down[2] = {nullptr, nullptr};
+    float* fstage[2] = {nullptr, nullptr};      // n*3 each: external force uploads
+    float* sstage[2] = {nullptr, nullptr};      // n*6 each: exported position + velocity
+    long long up_i = 0, down_i = 0;
 };
+
+static int ensure_copy_stream(MisSim* s) {
+    if (s->copy_stream) return MIS_OK;
+    CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&s->up_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; k++) {
+        CK(cudaEventCreateWithFlags(&s->ev_up[k], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s->ev_up_used[k], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s->ev_exp[k], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&s->ev_down[k], cudaEventDisableTiming));
+        CK(cudaMalloc((void**)&s->fstage[k], 3 * (size_t)s->n * sizeof(float) + 64));
+        CK(cudaMalloc((void**)&s->sstage[k], 6 * (size_t)s->n * sizeof(float) + 64));
+    }
+    return MIS_OK;
+}
 
 template <typename T>
 static cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(T) + 64); }
@@ -206,6 +226,15 @@ extern "C" int mis_create(int n, const float* x0_dev, const MisParams* params, v
 extern "C" int mis_destroy(MisSim* s) {
     if (!s) return MIS_OK;
     drop_graph(s);
+    if (s->copy_stream) {
+        cudaStreamSynchronize(s->copy_stream);
+        for (int k = 0; k < 2; k++) {
+            cudaEventDestroy(s->ev_up[k]); cudaEventDestroy(s->ev_up_used[k]); cudaEventDestroy(s->ev_exp[k]); cudaEventDestroy(s->ev_down[k]);
+            cudaFree(s->fstage[k]); cudaFree(s->sstage[k]);
+        }
+        cudaStreamDestroy(s->copy_stream);
+        if (s->up_stream) { cudaStreamSynchronize(s->up_stream); cudaStreamDestroy(s->up_stream); }
+    }
     void* ptrs[] = {s->con_idx, s->con_idx2, s->con_count, s->con_pts, s->con_pts2, s->con_s0, s->fcon, s->x0_orig, s->coords, s->cell_index, s->keys, s->subkey, s->Ks, s->perm, s->inv_perm, s->rs.keys_alt, s->rs.vals_alt,
                     s->rs.hist, s->rs.hist_scanned, s->rs.tile_tmp, s->bounds_dev, s->max_k_dev, s->cell_start, s->cell_end,
                     s->cell_lin_sorted, s->nbr_count, s->nbr_start, s->scan_tmp, s->nbr, s->cl_count, s->cl_start, s->cl, s->x0m, s->xv[0], s->xv[1], s->vel,
@@ -415,8 +444,19 @@ extern "C" int mis_set_ext_force(MisSim* s, const float* f_dev, void* stream) {
 
 extern "C" int mis_set_ext_force_host(MisSim* s, const float* f_host, void* stream) {
     if (!s || !f_host) return fail(MIS_E_INVALID, "null argument");
-    CK(cudaMemcpyAsync(s->stage, f_host, 3 * (size_t)s->n * sizeof(float), cudaMemcpyHostToDevice, (cudaStream_t)stream));
-    return mis_set_ext_force(s, s->stage, stream);
+    // upload on the copy stream (overlaps the kernels still running on `stream`), then gather on `stream`
+    int rc = ensure_copy_stream(s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int k = (int)(s->up_i++ & 1);
+    CK(cudaStreamWaitEvent(s->up_stream, s->ev_up_used[k], 0));         // the gather that last read this staging slot has run
+    CK(cudaMemcpyAsync(s->fstage[k], f_host, 3 * (size_t)s->n * sizeof(float), cudaMemcpyHostToDevice, s->up_stream));
+    CK(cudaEventRecord(s->ev_up[k], s->up_stream));
+    CK(cudaStreamWaitEvent(st, s->ev_up[k], 0));
+    rc = mis_set_ext_force(s, s->fstage[k], stream);
+    if (rc) return rc;
+    CK(cudaEventRecord(s->ev_up_used[k], st));
+    return MIS_OK;
 }
 
 extern "C" int mis_set_dirichlet(MisSim* s, const float* free_dev, void* stream) {
@@ -621,6 +661,39 @@ extern "C" int mis_get_state_host(MisSim* s, float* x_host, float* v_host, void*
     if (rc) return rc;
     if (x_host) CK(cudaMemcpyAsync(x_host, s->stage, N3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (v_host) CK(cudaMemcpyAsync(v_host, s->stage + N3, N3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return MIS_OK;
+}
+
+// Streaming export: the un-permute kernels run on `stream`, the device->host copies on the library's copy stream, so the
+// next step's kernels overlap the transfer.  Two exports may be in flight (double-buffered staging).
+extern "C" int mis_get_state_host_async(MisSim* s, float* x_host, float* v_host, void* stream) {
+    if (!s || (!x_host && !v_host)) return fail(MIS_E_INVALID, "null argument");
+    int rc = ensure_copy_stream(s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int k = (int)(s->down_i++ & 1);
+    const size_t N3 = 3 * (size_t)s->n;
+    CK(cudaStreamWaitEvent(st, s->ev_down[k], 0));                      // the copy that last read this staging slot has finished
+    rc = mis_get_state(s, x_host ? s->sstage[k] : nullptr, v_host ? s->sstage[k] + N3 : nullptr, stream);
+    if (rc) return rc;
+    CK(cudaEventRecord(s->ev_exp[k], st));
+    CK(cudaStreamWaitEvent(s->copy_stream, s->ev_exp[k], 0));
+    if (x_host) CK(cudaMemcpyAsync(x_host, s->sstage[k], N3 * sizeof(float), cudaMemcpyDeviceToHost, s->copy_stream));
+    if (v_host) CK(cudaMemcpyAsync(v_host, s->sstage[k] + N3, N3 * sizeof(float), cudaMemcpyDeviceToHost, s->copy_stream));
+    CK(cudaEventRecord(s->ev_down[k], s->copy_stream));
+    return MIS_OK;
+}
+
+// Blocks the host until at most `pending_allowed` (0 or 1) of the exports issued by mis_get_state_host_async are still in flight.
+extern "C" int mis_wait_state_host(MisSim* s, int pending_allowed) {
+    if (!s || pending_allowed < 0 || pending_allowed > 1) return fail(MIS_E_INVALID, "bad argument");
+    if (!s->copy_stream || s->down_i == 0) return MIS_OK;
+    if (pending_allowed == 0) {
+        CK(cudaEventSynchronize(s->ev_down[(s->down_i - 1) & 1]));
+        if (s->down_i >= 2) CK(cudaEventSynchronize(s->ev_down[s->down_i & 1]));
+    } else if (s->down_i >= 2) {
+        CK(cudaEventSynchronize(s->ev_down[s->down_i & 1]));            // slot of export down_i - 2
+    }
     return MIS_OK;
 }
 

@@ -95,6 +95,8 @@ SYMBOLS = {
     "mis_step": (C.c_int, [_vp, C.c_int, _vp]),
     "mis_get_state": (C.c_int, [_vp, _fp, _fp, _vp]),
     "mis_get_state_host": (C.c_int, [_vp, _fp, _fp, _vp]),
+    "mis_get_state_host_async": (C.c_int, [_vp, _fp, _fp, _vp]),
+    "mis_wait_state_host": (C.c_int, [_vp, C.c_int]),
     "mis_get_fields": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp]),
     "mis_eval_forces": (C.c_int, [_vp, _fp, _fp, _vp]),
     "mis_launch_count": (C.c_longlong, [_vp]),

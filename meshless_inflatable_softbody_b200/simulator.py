@@ -228,6 +228,16 @@ class Simulator:
         native.check(self.L.mis_get_state_host(self._h, x_host.data_ptr(), v_host.data_ptr() if v_host is not None else None,
                                                self._st()), "mis_get_state_host")
 
+    def get_state_host_async(self, x_host: torch.Tensor, v_host: Optional[torch.Tensor] = None):
+        """Streaming export into pinned host tensors: returns at once; the copy overlaps the following steps.
+        The tensors are valid after wait_state_host() (at most two exports may be in flight)."""
+        native.check(self.L.mis_get_state_host_async(self._h, x_host.data_ptr(), v_host.data_ptr() if v_host is not None else None,
+                                                     self._st()), "mis_get_state_host_async")
+
+    def wait_state_host(self, pending_allowed: int = 0):
+        """Block until at most `pending_allowed` (0 or 1) streaming exports are still in flight."""
+        native.check(self.L.mis_wait_state_host(self._h, int(pending_allowed)), "mis_wait_state_host")
+
     def fields(self, want=("R", "F", "S", "fel", "rho", "vol")):
         out = {}
         shapes = {"A": (self.n, 3, 3), "R": (self.n, 3, 3), "F": (self.n, 3, 3), "S": (self.n, 3, 3),

@@ -70,6 +70,21 @@ __device__ __forceinline__ float group_sum(float v) {
 #define MIS_STEP_MIN_BLOCKS 1
 #endif
 constexpr int STEP_THREADS = MIS_STEP_THREADS;
+#ifndef MIS_IDX_AHEAD
+#define MIS_IDX_AHEAD 2
+#endif
+constexpr int IDX_AHEAD = MIS_IDX_AHEAD;
+// union-list entries are read once per launch.  Keeping them out of L1 (MIS_IDX_NOALLOC) was measured SLOWER on B200
+// (deform 155 vs 145 us at n = 1e5): the default is a plain cached load.
+__device__ __forceinline__ uint32_t ld_idx(const uint32_t* p) {
+#ifdef MIS_IDX_NOALLOC
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}     // union-list indices are fetched this many entries (of one lane) ahead; even, >= 2
 
 // ---------------------------------------------------------------- union lists
 // One thread per cluster walks the 27 cells around each distinct member cell (cells already
@@ -242,18 +257,10 @@ __global__ void __launch_bounds__(STEP_THREADS, MIS_STEP_MIN_BLOCKS) k_deform_c(
 #pragma unroll
         for (int k = 0; k < 9; k++) { A[p][k] = 0.f; B[p][k] = 0.f; }
 
-    // two-stage software pipeline: the gathers of entry k+G are in flight while entry k is consumed
-    int k = gl;
-    uint32_t j1 = (k + G < cnt) ? lst[k + G] : 0u;
-    DeformJ d;
-    {
-        const uint32_t j0 = (k < cnt) ? lst[k] : 0u;
-        d.p0 = x0m[j0]; d.px = xcur[j0];
-    }
-    while (k < cnt) {
-        DeformJ dn;
-        dn.p0 = x0m[j1]; dn.px = xcur[j1];
-        const uint32_t j2 = (k + 2 * G < cnt) ? lst[k + 2 * G] : 0u;
+    // Software pipeline: indices are fetched IDX_AHEAD entries ahead (2, 4 and 8 measured the same on B200: the index stream is not
+    // what the loop waits for); the gathered record of entry k + G is in flight while entry k is consumed.  Unrolled by two (dA: even entries of this lane,
+    // dB: odd ones) so the in-flight record is never moved between registers.  The lists are padded with 64 zero entries.
+    auto eval = [&](const DeformJ& d) {
 #pragma unroll
         for (int p = 0; p < C; p++) {
             const float d0x = d.p0.x - p0i[p].x, d0y = d.p0.y - p0i[p].y, d0z = d.p0.z - p0i[p].z;
@@ -274,7 +281,30 @@ __global__ void __launch_bounds__(STEP_THREADS, MIS_STEP_MIN_BLOCKS) k_deform_c(
                 B[p][6] += dz * gx; B[p][7] += dz * gy; B[p][8] += dz * gz;
             }
         }
-        d = dn; j1 = j2; k += G;
+    };
+    {
+        int k = gl;
+        uint32_t q[IDX_AHEAD];                                  // q[t] = index of entry k + (t + 1) G
+#pragma unroll
+        for (int t = 0; t < IDX_AHEAD; t++) q[t] = (k + (t + 1) * G < cnt) ? ld_idx(lst + k + (t + 1) * G) : 0u;
+        DeformJ dA, dB;
+        {
+            const uint32_t j0 = (k < cnt) ? ld_idx(lst + k) : 0u;
+            dA.p0 = x0m[j0]; dA.px = xcur[j0];
+        }
+        while (k < cnt) {
+            dB.p0 = x0m[q[0]]; dB.px = xcur[q[0]];            // entry k + G
+            const uint32_t n0 = (k + (IDX_AHEAD + 1) * G < cnt) ? ld_idx(lst + k + (IDX_AHEAD + 1) * G) : 0u;
+            eval(dA);
+            if (k + G >= cnt) break;
+            dA.p0 = x0m[q[1]]; dA.px = xcur[q[1]];            // entry k + 2G
+            const uint32_t n1 = (k + (IDX_AHEAD + 2) * G < cnt) ? ld_idx(lst + k + (IDX_AHEAD + 2) * G) : 0u;
+            eval(dB);
+#pragma unroll
+            for (int t = 0; t + 2 < IDX_AHEAD; t++) q[t] = q[t + 2];
+            q[IDX_AHEAD - 2] = n0; q[IDX_AHEAD - 1] = n1;
+            k += 2 * G;
+        }
     }
 #pragma unroll
     for (int p = 0; p < C; p++)
@@ -456,7 +486,7 @@ __device__ __forceinline__ void integrate_epilogue(const View& s, const Consts& 
 //         = 0.5 V_i [ sum_j V_j R_j F_i S_j nabla_W_ij  +  R_i F_i S_i G_i ],  G_i = sum_j V_j nabla_W_ij (static)
 // (F_i, not F_j, multiplies S_j: sim.py:233.)  SYM = true is sim_taichi.py:147-158, where f_ij uses
 // F_j: force_i = 0.5 V_i [ sum_j V_j R_j F_j S_j nabla_W_ij + R_i F_i S_i G_i ] (antisymmetric pair term).
-struct ForceJ { float4 p0, r0, r1, r2, r3; };
+struct ForceJ { float4 p0, r0, r1, r2, r3, f0, f1, f2; };   // f0..f2 (F_j) are only loaded by the symmetric (sim_taichi.py) pair force
 
 template <int C, int G, bool SYM>
 __global__ void __launch_bounds__(STEP_THREADS, MIS_STEP_MIN_BLOCKS) k_force_c(View s, Consts c, int mode) {
@@ -493,19 +523,14 @@ __global__ void __launch_bounds__(STEP_THREADS, MIS_STEP_MIN_BLOCKS) k_force_c(V
 #pragma unroll
     for (int p = 0; p < C; p++) { a[p][0] = 0.f; a[p][1] = 0.f; a[p][2] = 0.f; }
 
-    int k = gl;
-    uint32_t j1 = (k + G < cnt) ? lst[k + G] : 0u;
-    uint32_t jc = (k < cnt) ? lst[k] : 0u;
-    ForceJ d;
-    d.p0 = x0m[jc]; d.r0 = RS0[jc]; d.r1 = RS1[jc]; d.r2 = RS2[jc]; d.r3 = RS3[jc];
-    while (k < cnt) {
-        ForceJ dn;
-        dn.p0 = x0m[j1]; dn.r0 = RS0[j1]; dn.r1 = RS1[j1]; dn.r2 = RS2[j1]; dn.r3 = RS3[j1];
-        const uint32_t j2 = (k + 2 * G < cnt) ? lst[k + 2 * G] : 0u;
+    auto load = [&](ForceJ& d, uint32_t j) {
+        d.p0 = x0m[j]; d.r0 = RS0[j]; d.r1 = RS1[j]; d.r2 = RS2[j]; d.r3 = RS3[j];
+        if (SYM) { d.f0 = Fd0[j]; d.f1 = Fd1[j]; d.f2 = Fd2[j]; }
+    };
+    auto eval = [&](const ForceJ& d) {
         float Fj[9];
         if (SYM) {
-            const float4 f0 = Fd0[jc], f1 = Fd1[jc], f2 = Fd2[jc];
-            Fj[0] = f0.x; Fj[1] = f0.y; Fj[2] = f0.z; Fj[3] = f0.w; Fj[4] = f1.x; Fj[5] = f1.y; Fj[6] = f1.z; Fj[7] = f1.w; Fj[8] = f2.x;
+            Fj[0] = d.f0.x; Fj[1] = d.f0.y; Fj[2] = d.f0.z; Fj[3] = d.f0.w; Fj[4] = d.f1.x; Fj[5] = d.f1.y; Fj[6] = d.f1.z; Fj[7] = d.f1.w; Fj[8] = d.f2.x;
         }
 #pragma unroll
         for (int p = 0; p < C; p++) {
@@ -526,7 +551,28 @@ __global__ void __launch_bounds__(STEP_THREADS, MIS_STEP_MIN_BLOCKS) k_force_c(V
             a[p][1] += d.r0.w * ux + d.r1.x * uy + d.r1.y * uz;
             a[p][2] += d.r1.z * ux + d.r1.w * uy + d.r2.x * uz;
         }
-        d = dn; jc = j1; j1 = j2; k += G;
+    };
+    {
+        // same pipeline as k_deform_c: indices IDX_AHEAD entries ahead, one gathered record in flight, unrolled by two
+        int k = gl;
+        uint32_t q[IDX_AHEAD];
+#pragma unroll
+        for (int t = 0; t < IDX_AHEAD; t++) q[t] = (k + (t + 1) * G < cnt) ? ld_idx(lst + k + (t + 1) * G) : 0u;
+        ForceJ dA, dB;
+        load(dA, (k < cnt) ? ld_idx(lst + k) : 0u);
+        while (k < cnt) {
+            load(dB, q[0]);
+            const uint32_t n0 = (k + (IDX_AHEAD + 1) * G < cnt) ? ld_idx(lst + k + (IDX_AHEAD + 1) * G) : 0u;
+            eval(dA);
+            if (k + G >= cnt) break;
+            load(dA, q[1]);
+            const uint32_t n1 = (k + (IDX_AHEAD + 2) * G < cnt) ? ld_idx(lst + k + (IDX_AHEAD + 2) * G) : 0u;
+            eval(dB);
+#pragma unroll
+            for (int t = 0; t + 2 < IDX_AHEAD; t++) q[t] = q[t + 2];
+            q[IDX_AHEAD - 2] = n0; q[IDX_AHEAD - 1] = n1;
+            k += 2 * G;
+        }
     }
 #pragma unroll
     for (int p = 0; p < C; p++) {

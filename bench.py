@@ -12,7 +12,8 @@ Workloads
           a DeepSDF-encoded obstacle (the reference's 9 x 1024 architecture, deepsdf.py:12-38, with analytic octahedron
           weights) standing on the ground plane; contact = ground penalty (sim.py:238-244) + SDF penalty (extension).
   N > 1 : one scene of N x (--n) particles (a beam, long axis x) slab-partitioned across the N GPUs with a per-step
-          NCCL halo exchange of the ghost particles' new positions (slab.py); per-GPU work is fixed => "scaling": "weak".
+          halo exchange of the ghost particles' new positions (slab.py: fused P2P push over NVLink peer memory, or NCCL
+          send/recv with --halo nccl); per-GPU work is fixed => "scaling": "weak".
           --mode batch runs independent scenes, one per GPU (configs[3]); --mode strong fixes the total particle count.
 
 Prints ONE JSON line on rank 0.
@@ -155,9 +156,9 @@ def workload_config(args, n_total, mean_k, world, mode, extra=None):
     elif mode == "batch":
         wl = "BASELINE configs[3] shape: independent ~%d-particle scenes, one per GPU, no communication" % args.n
     elif mode == "strong":
-        wl = "BASELINE configs[4] shape: one %d-particle elongated body slab-partitioned across %d GPUs, NCCL halo exchange per step" % (n_total, world)
+        wl = "BASELINE configs[4] shape: one %d-particle elongated body slab-partitioned across %d GPUs, halo exchange of ghost positions every step" % (n_total, world)
     else:
-        wl = ("one %d-particle elongated body (%d per GPU) slab-partitioned across %d GPUs, NCCL halo exchange of ghost positions "
+        wl = ("one %d-particle elongated body (%d per GPU) slab-partitioned across %d GPUs, halo exchange of ghost positions "
               "every step (BASELINE configs[4] mechanism at fixed per-GPU size)" % (n_total, args.n, world))
     c = {"workload": wl, "n_particles": int(n_total), "mean_neighbors": mean_k, "spacing_h": 0.5, "h": 0.007, "dt": 5e-5,
          "scene": "reference defaults E=1.5e5 nu=0.4 m=1e-4 x=-1, v0=(0,-0.4,0)", "mode": mode,
@@ -262,12 +263,14 @@ def run_ours(args, cfg, rank, world, local_rank):
         n_total = args.n * world if mode == "slab" else args.n_total
         x0 = beam_scene(n_total, seed=0, world=world)
         n_total = len(x0)
-        stepper = SlabSimulator(x0, cfg, rank=rank, world_size=world, device=str(dev),
+        stepper = SlabSimulator(x0, cfg, rank=rank, world_size=world, device=str(dev), halo=args.halo,
                                 lanes_per_particle=args.lanes, cluster_size=args.cluster)
         core = stepper.sim
         n_local, n_total_local = stepper.n_owned, core.n
-        extra = {"owned_per_gpu": n_local, "ghosts_per_gpu": n_total_local - n_local,
-                 "halo_bytes_per_step_per_gpu": 12 * int(sum(len(v) for v in stepper.plan.send.values()))}
+        extra = {"halo": ("fused P2P push over NVLink peer memory from the force kernel's epilogue + epoch flags, inside the step graph"
+                          if stepper.halo == "p2p" else "NCCL send/recv after every step"),
+                 "owned_per_gpu": n_local, "ghosts_per_gpu": n_total_local - n_local,
+                 "halo_bytes_per_step_per_gpu": (16 if stepper.halo == "p2p" else 12) * int(sum(len(v) for v in stepper.plan.send.values()))}
     info = core.neighbor_info()
     mean_k = info.total_pairs / core.n
     stepper.startup()
@@ -361,6 +364,8 @@ def run_ours(args, cfg, rank, world, local_rank):
         core.synchronize()
     ms_e2e_sync = timed(e2e_sync, core.synchronize)
     assert bool(torch.isfinite(x_host[0]).all()) and bool(torch.isfinite(x_host[1]).all()), "state diverged"
+    if mode in ("slab", "strong"):
+        assert stepper.halo_ok(), "a halo flag wait timed out"
 
     # ---- roofline of the dominant kernel: CUDA events around every launch (library stream), L2 warm
     peaks, peak_src = measured_peaks()
@@ -446,6 +451,7 @@ def main():
     ap.add_argument("--n", type=int, default=100_000, help="particles per GPU")
     ap.add_argument("--n-total", type=int, default=10_000_000, help="total particles for --mode strong")
     ap.add_argument("--mode", default="slab", choices=["slab", "batch", "strong"], help="multi-GPU workload (N > 1)")
+    ap.add_argument("--halo", default="auto", choices=["auto", "p2p", "nccl"], help="slab modes: ghost exchange mechanism")
     ap.add_argument("--lanes", type=int, default=0, help="lanes per cluster (0 = library default)")
     ap.add_argument("--cluster", type=int, default=0, help="particles per cluster (0 = library default)")
     ap.add_argument("--no-obstacle", action="store_true", help="N = 1: ground-plane contact only")

@@ -141,6 +141,41 @@ int mis_wait_state_host(MisSim* sim, int pending_allowed);
  * a rank sends the new positions of its boundary particles and overwrites its ghosts' before the next step. */
 int mis_gather_next_positions(MisSim* sim, const int* ids_dev, int count, float* x_dev /* count*3 */, void* stream);
 int mis_scatter_next_positions(MisSim* sim, const int* ids_dev, int count, const float* x_dev /* count*3 */, void* stream);
+/* Ghost volumes of a slab-partitioned scene.  compute_v_i (sim.py:154-167) needs a particle's whole neighbourhood; an
+ * outer ghost does not have it locally, so its owner's V (static: a function of x0 and m only) is written over the local
+ * value once after mis_set_mass.  ids_dev: caller ids (int32), vol_dev[count].  Recomputes the static sums that use V.  */
+int mis_set_volumes(MisSim* sim, const int* ids_dev, int count, const float* vol_dev, void* stream);
+/* sorted slot (index into the library's cell-sorted arrays) of each caller id                   */
+int mis_export_slots(MisSim* sim, const int* ids_dev, int count, int* slots_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused halo push over NVLink peer memory (no reference counterpart; replaces the gather / NCCL send-recv / scatter
+ * round trip of mis_gather_next_positions + mis_scatter_next_positions).  The force kernel's part_1 epilogue
+ * (sim.py:247-251) stores the new position of an owned boundary particle into its own array AND straight into the
+ * ghost slot of every peer that mirrors it (P2P stores, overlapping the rest of the kernel); ghost slots are never
+ * written locally.  One single-block kernel per step then publishes an epoch flag to each peer (release, system
+ * scope) and waits for the peers' flags (acquire), so a whole chunk of steps -- pushes and synchronisation
+ * included -- is one CUDA graph with no host or NCCL involvement.
+ *   mis_halo_ipc_handles : 3 x 64 bytes = cudaIpcMemHandle_t of position buffer 0, position buffer 1, flag array.
+ *   mis_halo_local_ptrs  : the same three as raw device pointers (peers living in the same process).
+ *   mis_ipc_open / close : map a peer's handle into this process (cudaIpcOpenMemHandle, lazy peer access).
+ *   mis_halo_connect     : peer_xv0/xv1[p] = peer p's position buffers mapped here; peer_flag[p] = address of MY entry
+ *                          in peer p's flag array (its base + my index in its peer list; MIS_MAX_PEERS entries);
+ *                          push_*: for each (owned caller id, peer index, slot on that peer) triple the particle is
+ *                          mirrored there (at most two peers per particle); ghost_ids: local particles owned elsewhere.
+ *                          All ranks must have finished their set-up (host barrier) before the first step after connect.
+ *   mis_halo_status      : synchronises `stream`; err = 1 if a flag wait timed out (MIS_HALO_TIMEOUT_MS, default 20 s).  */
+#define MIS_MAX_PEERS 4
+int mis_halo_ipc_handles(MisSim* sim, unsigned char* out192);
+int mis_halo_local_ptrs(MisSim* sim, void** xv0, void** xv1, void** flags);
+int mis_ipc_open(const unsigned char* handle64, void** dev_ptr);
+int mis_ipc_close(void* dev_ptr);
+int mis_halo_connect(MisSim* sim, int n_peers, void* const* peer_xv0, void* const* peer_xv1, void* const* peer_flag,
+                     int n_push, const int* push_ids_dev, const int* push_peer_dev, const int* push_slot_dev,
+                     int n_ghost, const int* ghost_ids_dev, void* stream);
+int mis_halo_disconnect(MisSim* sim);
+int mis_halo_status(MisSim* sim, void* stream, int* err, long long* exchanges);
+
 /* Per-particle fields of the current frame, caller order; any pointer may be NULL.
  * A_pq (needs keep_fields), R = U V^T, def_grad, S = compute_sigma, elastic force,
  * rho, volume  (sim.py:154-235).                                                    */
@@ -178,9 +213,10 @@ int mis_sdf_destroy(MisSdf* sdf);
  * frame of `points` by forward differences of step fd_eps in model space (3 extra evaluations). */
 int mis_sdf_query(MisSdf* sdf, const float* points_dev, int n, const float* xform_host,
                   float* sdf_dev, float* grad_dev, float fd_eps, void* stream);
-/* Hidden-layer kernel choice (tests / tuning): 0 = automatic (split-K over 8-CTA clusters with a distributed-shared-memory
- * reduction when the row count is small or lives on the device -- the per-step contact query; persistent 128 x 256 tiles for
- * bulk queries), 1 = always split-K, 2 = always big tiles.  Both are correct for any row count.              */
+/* Hidden-layer kernel choice (tests / tuning): 0 = automatic (few rows or a device-side row count -- the per-step contact query:
+ * ALL hidden layers in one cooperative launch, split-K over 8-CTA clusters with a distributed-shared-memory reduction and a
+ * device-wide barrier between layers; bulk queries: persistent 128 x 256 tiles, one launch per layer), 1 = split-K, one launch per
+ * layer, 2 = always big tiles, 3 = always the one-launch chain.  All are correct for any row count.              */
 int mis_sdf_set_gemm_path(MisSdf* sdf, int path);
 /* kernels launched so far by this network / of which tcgen05 GEMM launches                    */
 long long mis_sdf_launch_count(MisSdf* sdf, long long* gemm_launches);

@@ -9,6 +9,7 @@
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -86,6 +87,20 @@ struct MisSim {
     int* con_count = nullptr;                 // [0] broad-phase candidates, [1] particles in the contact band
     float *con_pts = nullptr, *con_pts2 = nullptr, *con_s0 = nullptr;
     float4* fcon = nullptr;
+    // the contact chain only reads the positions of the new frame, like k_deform_c: it runs beside it on a forked,
+    // higher-priority stream (a parallel branch of the step graph) and joins before k_force_c
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool serial_contact = false;
+    // fused halo push (slab-partitioned scenes)
+    int2* push = nullptr;                       // per-slot destination codes
+    unsigned* halo_mem = nullptr;               // [0..MIS_MAX_PEERS) flags written by the peers, [MIS_MAX_PEERS] epoch, [MIS_MAX_PEERS + 1] error
+    int halo_peers = 0;
+    bool halo_on = false;
+    float4* peer_xv[2][MIS_MAX_PEERS] = {};
+    unsigned* peer_flag[MIS_MAX_PEERS] = {};
+    unsigned long long halo_timeout_ns = 20000000000ull;
+    long long exchanges = 0;              // MIS_SERIAL_CONTACT=1: deform -> contact -> force in one stream (A/B measurement)
     // host <-> device streaming on a second stream (copy engines overlap the step kernels): double-buffered staging
     cudaStream_t copy_stream = nullptr;         // device -> host
     cudaStream_t up_stream = nullptr;           // host -> device (separate, so an upload never queues behind a download that waits for a step)
@@ -153,6 +168,8 @@ static View make_view(MisSim* s) {
     v.RS = s->RS; v.Fd = s->Fd; v.Ks = s->Ks; v.Apq = s->p.keep_fields ? s->Apq : nullptr;
     v.cl_start = s->cl_start; v.cl = s->cl;
     v.fcon = s->sdf ? s->fcon : nullptr;
+    v.push = s->halo_on ? s->push : nullptr;
+    for (int p = 0; p < 4; p++) v.peer_x[p] = s->halo_on ? s->peer_xv[s->cur ^ 1][p] : nullptr;
     return v;
 }
 
@@ -226,6 +243,11 @@ extern "C" int mis_create(int n, const float* x0_dev, const MisParams* params, v
 extern "C" int mis_destroy(MisSim* s) {
     if (!s) return MIS_OK;
     drop_graph(s);
+    if (s->side_stream) {
+        cudaStreamSynchronize(s->side_stream);
+        cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join);
+        cudaStreamDestroy(s->side_stream);
+    }
     if (s->copy_stream) {
         cudaStreamSynchronize(s->copy_stream);
         for (int k = 0; k < 2; k++) {
@@ -235,7 +257,7 @@ extern "C" int mis_destroy(MisSim* s) {
         cudaStreamDestroy(s->copy_stream);
         if (s->up_stream) { cudaStreamSynchronize(s->up_stream); cudaStreamDestroy(s->up_stream); }
     }
-    void* ptrs[] = {s->con_idx, s->con_idx2, s->con_count, s->con_pts, s->con_pts2, s->con_s0, s->fcon, s->x0_orig, s->coords, s->cell_index, s->keys, s->subkey, s->Ks, s->perm, s->inv_perm, s->rs.keys_alt, s->rs.vals_alt,
+    void* ptrs[] = {s->push, s->halo_mem, s->con_idx, s->con_idx2, s->con_count, s->con_pts, s->con_pts2, s->con_s0, s->fcon, s->x0_orig, s->coords, s->cell_index, s->keys, s->subkey, s->Ks, s->perm, s->inv_perm, s->rs.keys_alt, s->rs.vals_alt,
                     s->rs.hist, s->rs.hist_scanned, s->rs.tile_tmp, s->bounds_dev, s->max_k_dev, s->cell_start, s->cell_end,
                     s->cell_lin_sorted, s->nbr_count, s->nbr_start, s->scan_tmp, s->nbr, s->cl_count, s->cl_start, s->cl, s->x0m, s->xv[0], s->xv[1], s->vel,
                     s->f1, s->fel, s->fext, s->freem, s->matl, s->RS, s->Fd, s->Apq, s->scratch4, s->stage};
@@ -468,8 +490,11 @@ extern "C" int mis_set_dirichlet(MisSim* s, const float* free_dev, void* stream)
 }
 
 // ------------------------------------------------------------------ step machinery
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e && e[0] ? atoi(e) : dflt; }
 template <int C, int G> static void launch_deform(MisSim* s, const View& v, cudaStream_t st) {
     const int nc = (s->n + C - 1) / C;
+    static int carve = -2;                    // tuning hook: MIS_DEFORM_CARVEOUT = preferred shared-memory carve-out in percent
+    if (carve == -2) { carve = env_int("MIS_DEFORM_CARVEOUT", -1); if (carve >= 0) cudaFuncSetAttribute(k_deform_c<C, G, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve); }
     k_deform_c<C, G, false><<<nblk((long long)nc * G, STEP_THREADS), STEP_THREADS, 0, st>>>(v, s->c);
 }
 template <int C> static void launch_deform2(MisSim* s, const View& v, cudaStream_t st) {
@@ -512,6 +537,20 @@ static void enqueue_force(MisSim* s, const View& v, int mode, cudaStream_t st) {
     s->launches++;
 }
 
+// after a kernel that pushed new positions to the peers: publish this rank's epoch, wait for the peers'
+static void enqueue_halo_sync(MisSim* s, cudaStream_t st) {
+    if (!s->halo_on) return;
+    HaloSync h;
+    h.n_peers = s->halo_peers;
+    h.epoch = s->halo_mem + MIS_MAX_PEERS;
+    h.my_flags = s->halo_mem;
+    for (int p = 0; p < 4; p++) h.peer_flag[p] = s->peer_flag[p];
+    h.err = (int*)(s->halo_mem + MIS_MAX_PEERS + 1);
+    h.timeout_ns = s->halo_timeout_ns;
+    k_halo_sync<<<1, 32, 0, st>>>(h);
+    s->launches++; s->exchanges++;
+}
+
 // obstacle contact at the now-current positions: broad phase (bounding box) -> MLP values -> narrow phase (contact band)
 // -> three forward-difference evaluations of the particles in contact -> penalty force.  No host synchronisation:
 // the live row counts stay on the device and dead row-blocks of the GEMM grid exit at once.
@@ -538,6 +577,21 @@ static void enqueue_contact(MisSim* s, const View& v, cudaStream_t st) {
     s->launches += 3 + (net->launches - l0);
 }
 
+// k_deform_c and the contact chain of one frame: both depend on the new positions only
+static void enqueue_deform_contact(MisSim* s, const View& v, cudaStream_t st) {
+    if (s->sdf && s->side_stream && !s->serial_contact) {
+        cudaEventRecord(s->ev_fork, st);
+        cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0);
+        enqueue_contact(s, v, s->side_stream);
+        cudaEventRecord(s->ev_join, s->side_stream);
+        enqueue_deform(s, v, st);
+        cudaStreamWaitEvent(st, s->ev_join, 0);
+    } else {
+        enqueue_deform(s, v, st);
+        enqueue_contact(s, v, st);
+    }
+}
+
 // frame-0 style priming at the current x: elastic force, force_1 and the next position
 static int prime(MisSim* s, cudaStream_t st) {
     if (!s->mass_set || !s->material_set) return fail(MIS_E_STATE, "set_mass and set_material must precede startup/step");
@@ -549,10 +603,10 @@ static int prime(MisSim* s, cudaStream_t st) {
             k_reintegrate<<<nblk(s->n, 256), 256, 0, st>>>(v, s->c);
             s->launches++;
         } else {
-            enqueue_deform(s, v, st);
-            enqueue_contact(s, v, st);
+            enqueue_deform_contact(s, v, st);
             enqueue_force(s, v, MODE_PRIME, st);
         }
+        enqueue_halo_sync(s, st);
         CK_LAUNCH();
     }
     s->dirty = false; s->forces_only = false;
@@ -583,16 +637,15 @@ static void enqueue_one_step(MisSim* s, cudaStream_t st) {
     if (s->p.euler) {
         // sim_taichi.py:174-182: forces at frame f, then advance to f+1
         View v = make_view(s);
-        enqueue_deform(s, v, st);
-        enqueue_contact(s, v, st);
+        enqueue_deform_contact(s, v, st);
         enqueue_force(s, v, MODE_EULER, st);
         s->cur ^= 1;
     } else {
         s->cur ^= 1;                       // part_1 of this step was fused into the previous force kernel
         View v = make_view(s);
-        enqueue_deform(s, v, st);
-        enqueue_contact(s, v, st);
+        enqueue_deform_contact(s, v, st);
         enqueue_force(s, v, MODE_STEP, st);
+        enqueue_halo_sync(s, st);
     }
 }
 
@@ -756,6 +809,131 @@ extern "C" int mis_scatter_next_positions(MisSim* s, const int* ids_dev, int cou
     return MIS_OK;
 }
 
+extern "C" int mis_set_volumes(MisSim* s, const int* ids_dev, int count, const float* vol_dev, void* stream) {
+    if (!s || count < 0 || (count > 0 && (!ids_dev || !vol_dev))) return fail(MIS_E_INVALID, "bad argument");
+    if (!s->mass_set) return fail(MIS_E_STATE, "mis_set_volumes before mis_set_mass");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (count > 0) {
+        k_set_volumes<<<nblk(count, 256), 256, 0, st>>>(s->xv[0], s->xv[1], s->inv_perm, ids_dev, count, vol_dev);
+        s->launches++;
+    }
+    const int blocks = nblk((long long)s->n * s->G, STEP_THREADS);
+    if (s->G == 8) k_static_K<8><<<blocks, STEP_THREADS, 0, st>>>(s->x0m, s->xv[0], s->nbr_start, s->nbr, s->n, s->c, s->Ks);
+    else if (s->G == 16) k_static_K<16><<<blocks, STEP_THREADS, 0, st>>>(s->x0m, s->xv[0], s->nbr_start, s->nbr, s->n, s->c, s->Ks);
+    else k_static_K<32><<<blocks, STEP_THREADS, 0, st>>>(s->x0m, s->xv[0], s->nbr_start, s->nbr, s->n, s->c, s->Ks);
+    CK_LAUNCH(); s->launches++;
+    s->dirty = true; s->forces_only = false;
+    return MIS_OK;
+}
+
+extern "C" int mis_export_slots(MisSim* s, const int* ids_dev, int count, int* slots_dev, void* stream) {
+    if (!s || count < 0 || (count > 0 && (!ids_dev || !slots_dev))) return fail(MIS_E_INVALID, "bad argument");
+    if (count == 0) return MIS_OK;
+    k_slots_of<<<nblk(count, 256), 256, 0, (cudaStream_t)stream>>>(s->inv_perm, ids_dev, count, slots_dev);
+    CK_LAUNCH(); s->launches++;
+    return MIS_OK;
+}
+
+// ------------------------------------------------------------------ fused halo push over peer memory
+static int ensure_halo_mem(MisSim* s) {
+    if (s->halo_mem) return MIS_OK;
+    CK(cudaMalloc((void**)&s->halo_mem, 64 * sizeof(unsigned)));
+    CK(cudaMemset(s->halo_mem, 0, 64 * sizeof(unsigned)));
+    return MIS_OK;
+}
+
+extern "C" int mis_halo_local_ptrs(MisSim* s, void** xv0, void** xv1, void** flags) {
+    if (!s) return fail(MIS_E_INVALID, "null sim");
+    int rc = ensure_halo_mem(s);
+    if (rc) return rc;
+    if (xv0) *xv0 = s->xv[0];
+    if (xv1) *xv1 = s->xv[1];
+    if (flags) *flags = s->halo_mem;
+    return MIS_OK;
+}
+
+extern "C" int mis_halo_ipc_handles(MisSim* s, unsigned char* out192) {
+    if (!s || !out192) return fail(MIS_E_INVALID, "null argument");
+    int rc = ensure_halo_mem(s);
+    if (rc) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    void* ptrs[3] = {s->xv[0], s->xv[1], s->halo_mem};
+    for (int k = 0; k < 3; k++) {
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, ptrs[k]));
+        memcpy(out192 + 64 * k, &h, 64);
+    }
+    return MIS_OK;
+}
+
+extern "C" int mis_ipc_open(const unsigned char* handle64, void** dev_ptr) {
+    if (!handle64 || !dev_ptr) return fail(MIS_E_INVALID, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return MIS_OK;
+}
+
+extern "C" int mis_ipc_close(void* dev_ptr) {
+    if (dev_ptr) CK(cudaIpcCloseMemHandle(dev_ptr));
+    return MIS_OK;
+}
+
+extern "C" int mis_halo_connect(MisSim* s, int n_peers, void* const* peer_xv0, void* const* peer_xv1, void* const* peer_flag,
+                                int n_push, const int* push_ids_dev, const int* push_peer_dev, const int* push_slot_dev,
+                                int n_ghost, const int* ghost_ids_dev, void* stream) {
+    if (!s || n_peers < 0 || n_peers > MIS_MAX_PEERS || n_push < 0 || n_ghost < 0) return fail(MIS_E_INVALID, "mis_halo_connect: bad argument");
+    if (n_peers > 0 && (!peer_xv0 || !peer_xv1 || !peer_flag)) return fail(MIS_E_INVALID, "mis_halo_connect: null peer table");
+    if (n_push > 0 && (!push_ids_dev || !push_peer_dev || !push_slot_dev)) return fail(MIS_E_INVALID, "mis_halo_connect: null push list");
+    if (n_ghost > 0 && !ghost_ids_dev) return fail(MIS_E_INVALID, "mis_halo_connect: null ghost list");
+    if (s->p.euler) return fail(MIS_E_UNSUPPORTED, "halo plumbing supports the velocity-Verlet path only");
+    if ((long long)s->n >= (1ll << PUSH_SLOT_BITS)) return fail(MIS_E_UNSUPPORTED, "halo push supports up to 2^28 particles per rank");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ensure_halo_mem(s);
+    if (rc) return rc;
+    if (!s->push) CK(dalloc(&s->push, (size_t)s->n));
+    CK(cudaMemsetAsync(s->push, 0xFF, (size_t)s->n * sizeof(int2), st));
+    const int m = n_push > n_ghost ? n_push : n_ghost;
+    if (m > 0) {
+        k_push_fill<<<nblk(m, 256), 256, 0, st>>>(s->push, s->inv_perm, n_push, push_ids_dev, push_peer_dev, push_slot_dev, n_ghost, ghost_ids_dev);
+        CK_LAUNCH(); s->launches++;
+    }
+    for (int p = 0; p < MIS_MAX_PEERS; p++) {
+        s->peer_xv[0][p] = p < n_peers ? (float4*)peer_xv0[p] : nullptr;
+        s->peer_xv[1][p] = p < n_peers ? (float4*)peer_xv1[p] : nullptr;
+        s->peer_flag[p] = p < n_peers ? (unsigned*)peer_flag[p] : nullptr;
+    }
+    s->halo_peers = n_peers;
+    s->halo_on = true;
+    const char* e = getenv("MIS_HALO_TIMEOUT_MS");
+    if (e && atof(e) > 0.0) s->halo_timeout_ns = (unsigned long long)(atof(e) * 1e6);
+    drop_graph(s);
+    s->dirty = true; s->forces_only = false;
+    CK(cudaStreamSynchronize(st));
+    return MIS_OK;
+}
+
+extern "C" int mis_halo_disconnect(MisSim* s) {
+    if (!s) return fail(MIS_E_INVALID, "null sim");
+    drop_graph(s);
+    s->halo_on = false; s->halo_peers = 0;
+    s->dirty = true; s->forces_only = false;
+    return MIS_OK;
+}
+
+extern "C" int mis_halo_status(MisSim* s, void* stream, int* err, long long* exchanges) {
+    if (!s) return fail(MIS_E_INVALID, "null sim");
+    if (err) *err = 0;
+    if (exchanges) *exchanges = s->exchanges;
+    if (!s->halo_mem) return MIS_OK;
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    unsigned host[2] = {0u, 0u};                                     // epoch, error flag
+    CK(cudaMemcpy(host, s->halo_mem + MIS_MAX_PEERS, sizeof host, cudaMemcpyDeviceToHost));
+    if (err) *err = (int)host[1];
+    if (exchanges) *exchanges = (long long)host[0];                  // counted on the device: graph replays included
+    return MIS_OK;
+}
+
 extern "C" long long mis_launch_count(MisSim* s) { return s ? s->launches : 0; }
 
 // n_steps steps launched one kernel at a time with a CUDA event pair around each launch on
@@ -775,7 +953,7 @@ extern "C" int mis_profile_step(MisSim* s, int n_steps, void* stream, double* ms
         CK(cudaEventRecord(ev[3 * k + 1], st));
         enqueue_force(s, v, s->p.euler ? MODE_EULER : MODE_STEP, st);
         CK(cudaEventRecord(ev[3 * k + 2], st));
-        if (s->p.euler) s->cur ^= 1;
+        if (s->p.euler) s->cur ^= 1; else enqueue_halo_sync(s, st);
     }
     CK(cudaStreamSynchronize(st));
     double a = 0, b = 0;
@@ -808,11 +986,31 @@ extern "C" int mis_sdf_create(int n_layers, const int* dims, const float* const*
     SALLOC(s->W0, (size_t)H * 3); SALLOC(s->b0, H); SALLOC(s->wl, H); SALLOC(s->bl, 1);
     k_sdf_pack_weights<<<H, 256, 0, st>>>(g_dev[0], v_dev[0], H, 3, s->W0, nullptr, nullptr);
     cudaMemcpyAsync(s->b0, bias_dev[0], H * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    const size_t hidden = (size_t)(n_layers - 2);
+    SALLOC(s->Wslab, hidden * 2 * (size_t)H * H);
+    {   // per-step contact query: the weights (hidden * 8 MB at H = 1024) are re-read every step while the gather kernels stream
+        // > 100 MB of neighbour lists through L2 in between; keep them in the persisting part of L2 (MIS_SDF_L2_PIN=0 disables)
+        const char* e = getenv("MIS_SDF_L2_PIN");
+        int dev = 0, max_persist = 0, max_win = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        const size_t need = hidden * 2 * (size_t)H * H * sizeof(float);
+        if (!(e && e[0] == '0') && max_persist > 0 && (size_t)max_win >= 2 * (size_t)H * H * sizeof(float)) {
+            size_t cur_lim = 0;
+            cudaDeviceGetLimit(&cur_lim, cudaLimitPersistingL2CacheSize);
+            const size_t want = need < (size_t)max_persist ? need : (size_t)max_persist;
+            if (cur_lim < want) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+            s->l2_pin = true;
+        }
+    }
+    SALLOC(s->bslab, hidden * (size_t)H);
+    { float* sy = nullptr; SALLOC(sy, 16); s->chain_sync = (unsigned*)sy; cudaMemsetAsync(sy, 0, 16 * sizeof(float), st); }
+    { const char* e = getenv("MIS_SDF_CHAIN"); if (e && e[0] == '0') s->chain_mode = 0; }
     for (int l = 1; l < n_layers - 1; l++) {
-        float *hi = nullptr, *lo = nullptr, *b = nullptr;
-        SALLOC(hi, (size_t)H * H); s->Whi.push_back(hi);
-        SALLOC(lo, (size_t)H * H); s->Wlo.push_back(lo);
-        SALLOC(b, H); s->bh.push_back(b);
+        float *hi = s->Wslab + (size_t)(l - 1) * 2 * H * H, *lo = hi + (size_t)H * H, *b = s->bslab + (size_t)(l - 1) * H;
+        s->Whi.push_back(hi); s->Wlo.push_back(lo);
+        s->bh.push_back(b);
         k_sdf_pack_weights<<<H, 256, 0, st>>>(g_dev[l], v_dev[l], H, H, nullptr, hi, lo);
         cudaMemcpyAsync(b, bias_dev[l], H * sizeof(float), cudaMemcpyDeviceToDevice, st);
     }
@@ -862,8 +1060,9 @@ extern "C" int mis_sdf_query(MisSdf* s, const float* points_dev, int n, const fl
 }
 
 extern "C" int mis_sdf_set_gemm_path(MisSdf* s, int path) {
-    if (!s || path < 0 || path > 2) return fail(MIS_E_INVALID, "mis_sdf_set_gemm_path: path must be 0, 1 or 2");
-    if (path == 1 && s->H > SK_MAX_KBS * SK_SPLIT * SDF_BK) return fail(MIS_E_UNSUPPORTED, "split-K kernel supports hidden widths up to 1024");
+    if (!s || path < 0 || path > 3) return fail(MIS_E_INVALID, "mis_sdf_set_gemm_path: path must be 0, 1, 2 or 3");
+    if (path == 3 && (s->H % CH_BN != 0 || s->H / CH_BN > 15)) return fail(MIS_E_UNSUPPORTED, "chain kernel supports hidden widths up to 1024");
+    if ((path == 1 || path == 3) && s->H > SK_MAX_KBS * SK_SPLIT * SDF_BK) return fail(MIS_E_UNSUPPORTED, "split-K kernel supports hidden widths up to 1024");
     s->force_path = path;
     return MIS_OK;
 }
@@ -917,6 +1116,15 @@ extern "C" int mis_set_sdf_contact(MisSim* s, MisSdf* sdf, const float* xform_ho
     if (!s->fcon) {
         CK(dalloc(&s->con_idx, N)); CK(dalloc(&s->con_idx2, N)); CK(dalloc(&s->con_count, (size_t)4));
         CK(dalloc(&s->con_pts, 3 * N)); CK(dalloc(&s->con_pts2, 3 * N)); CK(dalloc(&s->con_s0, N)); CK(dalloc(&s->fcon, N));
+    }
+    if (!s->side_stream) {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));                  // hi = numerically lowest = highest priority
+        CK(cudaStreamCreateWithPriority(&s->side_stream, cudaStreamNonBlocking, hi));
+        CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+        const char* e = getenv("MIS_SERIAL_CONTACT");
+        s->serial_contact = e && e[0] == '1';
     }
     CK(cudaMemsetAsync(s->con_count, 0, 4 * sizeof(int), (cudaStream_t)stream));
     CK(sdf_reserve(sdf, s->n));

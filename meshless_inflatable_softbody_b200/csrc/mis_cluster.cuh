@@ -52,7 +52,93 @@ struct View {
     const unsigned long long* cl_start;   // union list offsets per cluster
     const uint32_t* cl;                   // union lists (slot ids)
     const float4* fcon;                   // optional obstacle-contact force at the current positions (DeepSDF extension)
+    // fused halo push (slab-partitioned scenes): per slot two destination codes (peer << 28 | slot on that peer), -1 = none;
+    // .x == -2 marks a ghost slot, which only its owner's push may write.  peer_x[p] = the position buffer of the NEXT frame
+    // on peer p (peer-mapped memory, NVLink stores).
+    const int2* push;
+    float4* peer_x[4];
 };
+
+constexpr int PUSH_GHOST = -2;
+constexpr int PUSH_SLOT_BITS = 28;
+
+// new position of slot i: local store + stores into the ghost slots of the peers that mirror the particle
+__device__ __forceinline__ void store_next(const View& s, int i, float4 v) {
+    if (s.push) {
+        const int2 pc = s.push[i];
+        if (pc.x == PUSH_GHOST) return;
+        s.xnext[i] = v;
+        if (pc.x >= 0) s.peer_x[pc.x >> PUSH_SLOT_BITS][pc.x & ((1 << PUSH_SLOT_BITS) - 1)] = v;
+        if (pc.y >= 0) s.peer_x[pc.y >> PUSH_SLOT_BITS][pc.y & ((1 << PUSH_SLOT_BITS) - 1)] = v;
+    } else {
+        s.xnext[i] = v;
+    }
+}
+
+// One exchange = every rank publishes its epoch to its peers and waits for theirs.  Runs after the kernel that pushed
+// (stream order): the pushes are complete when this kernel starts; fence + release make them visible system-wide before
+// the flag.  A peer's pushes are visible here once its flag is (acquire).  Single block, thread p handles peer p.
+struct HaloSync {
+    int n_peers;
+    unsigned* epoch;                      // [0] exchanges done by this rank
+    unsigned* my_flags;                   // [p] last epoch published by peer p (written remotely)
+    unsigned* peer_flag[4];               // my entry in peer p's flag array (peer-mapped)
+    int* err;
+    unsigned long long timeout_ns;
+};
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__global__ void __launch_bounds__(32) k_halo_sync(HaloSync h) {
+    __shared__ unsigned e_s;
+    if (threadIdx.x == 0) {
+        const unsigned e = h.epoch[0] + 1u;
+        h.epoch[0] = e;
+        e_s = e;
+    }
+    __syncthreads();
+    const unsigned e = e_s;
+    if ((int)threadIdx.x < h.n_peers) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(h.peer_flag[threadIdx.x]), "r"(e) : "memory");
+        const unsigned long long t0 = global_ns();
+        const unsigned* f = h.my_flags + threadIdx.x;
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if ((int)(v - e) >= 0) break;
+            if (*(volatile int*)h.err) break;                                   // an earlier wait timed out: do not stall every later step
+            if (global_ns() - t0 > h.timeout_ns) { atomicExch(h.err, 1); break; }
+            __nanosleep(200);
+        }
+        __threadfence_system();
+    }
+}
+
+// per-slot push table from (caller id, peer, remote slot) triples and the ghost list
+__global__ void __launch_bounds__(256) k_push_fill(int2* __restrict__ push, const int* __restrict__ inv_perm, int n_push, const int* __restrict__ ids,
+                                                   const int* __restrict__ peer, const int* __restrict__ slot, int n_ghost, const int* __restrict__ ghost_ids) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_push) {
+        const int code = (peer[k] << PUSH_SLOT_BITS) | slot[k];
+        int* e = (int*)(push + inv_perm[ids[k]]);
+        if (atomicCAS(e, -1, code) != -1) atomicCAS(e + 1, -1, code);      // second mirror of the same particle
+    }
+    if (k < n_ghost) push[inv_perm[ghost_ids[k]]].x = PUSH_GHOST;
+}
+__global__ void __launch_bounds__(256) k_slots_of(const int* __restrict__ inv_perm, const int* __restrict__ ids, int count, int* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count) out[k] = inv_perm[ids[k]];
+}
+__global__ void __launch_bounds__(256) k_set_volumes(float4* __restrict__ xv0, float4* __restrict__ xv1, const int* __restrict__ inv_perm,
+                                                     const int* __restrict__ ids, int count, const float* __restrict__ vol) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int sl = inv_perm[ids[k]];
+    xv0[sl].w = vol[k]; xv1[sl].w = vol[k];
+}
 
 enum ForceMode { MODE_PRIME = 0, MODE_STEP = 1, MODE_EULER = 2, MODE_EVAL = 3 };
 
@@ -457,7 +543,7 @@ __device__ __forceinline__ void integrate_epilogue(const View& s, const Consts& 
         xn.z = __fadd_rn(x.z, __fmul_rn(__fmul_rn(c.dt, vn.z), fr.z));
         s.vel[i] = make_float4(vn.x, vn.y, vn.z, 0.f);
         s.fel[i] = make_float4(fel.x, fel.y, fel.z, 0.f);
-        s.xnext[i] = make_float4(xn.x, xn.y, xn.z, pxi.w);
+        store_next(s, i, make_float4(xn.x, xn.y, xn.z, pxi.w));
         return;
     }
     if (mode == MODE_STEP) {
@@ -477,7 +563,7 @@ __device__ __forceinline__ void integrate_epilogue(const View& s, const Consts& 
     xn.z = part1_axis(x.z, v.z, F1n.z, m, fr.z, c);
     s.f1[i] = make_float4(F1n.x, F1n.y, F1n.z, 0.f);
     s.fel[i] = make_float4(fel.x, fel.y, fel.z, 0.f);
-    s.xnext[i] = make_float4(xn.x, xn.y, xn.z, pxi.w);
+    store_next(s, i, make_float4(xn.x, xn.y, xn.z, pxi.w));
 }
 
 // ---------------------------------------------------------------- k_force_c

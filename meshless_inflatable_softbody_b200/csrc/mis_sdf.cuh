@@ -488,6 +488,235 @@ k_sdf_gemm_sk(const float* __restrict__ Xhi, const float* __restrict__ Xlo, cons
     SK_CTA(1);
 }
 
+// ---------------------------------------------------------------- ALL hidden layers of a few-row query in ONE launch
+// k_sdf_gemm_sk pays a launch, a pipeline fill and a drain per layer; at a few hundred rows those fixed latencies are the whole cost
+// (7 layers x ~14 us per pass of the per-step contact query).  k_sdf_chain_sk walks every hidden layer inside one launch:
+//   * decomposition: cluster c (8 CTAs) owns output columns [128 c, 128 c + 128), CTA rank r the K slice [K r / 8, K (r + 1) / 8)
+//     (split-K); the 8 partial 128 x 128 accumulators go TMEM -> shared memory and are reduced through distributed shared memory in
+//     FIXED rank order (deterministic, and the same order as k_sdf_gemm_sk: bit-identical results); rank r finishes 16 columns.
+//     H / 128 clusters = 64 CTAs at H = 1024: a cooperative launch accepts at most 15 co-resident 8-CTA clusters on a B200 (measured:
+//     cudaOccupancyMaxActiveClusters), which rules out the 16 clusters of 64-column tiles;
+//   * the grid meets at a device-wide barrier between layers: epilogue threads fence + count in, the TMA producer of every CTA waits
+//     for the count before it loads the new activations.  Cooperative launch => all CTAs are co-resident, the wait cannot deadlock;
+//   * the W tiles of the next layer's first k-blocks do not depend on the activations: they are issued into the ring BEFORE the barrier
+//     wait (same stage barrier; the A halves complete the transaction count afterwards);
+//   * the partial tile has its own 64 KB of shared memory, so the producer runs ahead of the epilogue; only the MMA issuer waits for the
+//     previous tile's epilogue (the accumulator is single-buffered).
+constexpr int CH_BN = 128;
+constexpr int CH_STAGES = 2;
+constexpr int CH_STAGE_BYTES = 4 * SDF_TILE_BYTES;                         // A_hi, A_lo, W_hi, W_lo of one k-block: 64 KB
+constexpr int CH_STAGING_BYTES = SDF_BM * CH_BN * 4;                       // 64 KB fp32 partial tile
+constexpr int CH_TMEM_COLS = 128;
+constexpr int CH_SMEM_BYTES = CH_STAGES * CH_STAGE_BYTES + CH_STAGING_BYTES + 256 + 1024;
+
+struct SkChain {
+    const float* W;          // hidden-layer weights, contiguous: layer l = [hi plane H*H | lo plane H*H] at W + l * 2 H H (UMMA tiles)
+    const float* bias;       // [n_layers][H]
+    float* act[2][2];        // ping-pong activations [buffer][hi / lo]; layer l reads buffer l & 1, writes (l + 1) & 1
+    int n_layers;
+    unsigned* sync;          // [0] device-wide barrier count, [1] exit count (the last CTA out zeroes both for the next launch)
+};
+
+__global__ void __cluster_dims__(SK_SPLIT, 1, 1) __launch_bounds__(SDF_THREADS, 1)
+k_sdf_chain_sk(SkChain c, int H, int m_rows, const int* __restrict__ m_count) {
+    extern __shared__ uint8_t smem_raw[];
+    const int nb = blockIdx.x / SK_SPLIT;                      // cluster id = column tile (gridDim.x = (H / 128) * 8 exactly)
+    const uint32_t rank = cluster_ctarank();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KB = H / SDF_BK;
+    const int kbs = KB / SK_SPLIT;                             // k-blocks of this rank
+    const int k0 = (int)rank * kbs;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t stg_sm = base + CH_STAGES * CH_STAGE_BYTES; // partial tile
+    const uint32_t bars = stg_sm + CH_STAGING_BYTES;
+    // full[s] +8 s | empty[s] +16 + 8 s | tfull +32 | stg_done +40 | ready +48 | freeb +56 | tmem pointer +64
+    const uint32_t BAR_F = bars, BAR_E = bars + 16, BAR_TF = bars + 32, BAR_SD = bars + 40, BAR_RDY = bars + 48, BAR_FREE = bars + 56,
+                   TMEM_SLOT = bars + 64;
+    volatile uint32_t* tmem_ptr_sm = reinterpret_cast<volatile uint32_t*>(smem_raw + (TMEM_SLOT - smem_u32(smem_raw)));
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CH_BN >> 3) << 17) | ((uint32_t)(SDF_BM >> 4) << 24);
+    const unsigned nctas = gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < CH_STAGES; s++) { mbar_init(BAR_F + 8 * s, 1); mbar_init(BAR_E + 8 * s, 1); }
+        mbar_init(BAR_TF, 1); mbar_init(BAR_SD, 4);
+        mbar_init(BAR_RDY, SK_SPLIT); mbar_init(BAR_FREE, SK_SPLIT);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(TMEM_SLOT), "r"((uint32_t)CH_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = *tmem_ptr_sm;
+    const int live = m_count ? min(*m_count, m_rows) : m_rows;
+    const int row_blocks = (live + SDF_BM - 1) / SDF_BM;       // uniform over the grid; 0: nothing to do but release TMEM
+    const int nl = row_blocks > 0 ? c.n_layers : 0;
+    const size_t HH = (size_t)H * H;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // W tile (rows [128 nb, 128 nb + 128), k-block kb) of layer l into the stage of ring position `pos`: waits for the stage, arms its barrier
+            auto issue_w = [&](int l, int kb, uint32_t pos) {
+                const uint32_t s = pos % CH_STAGES, ph = (pos / CH_STAGES) & 1;
+                mbar_wait(BAR_E + 8 * s, ph ^ 1);
+                const uint32_t full = BAR_F + 8 * s;
+                mbar_expect_tx(full, CH_STAGE_BYTES);
+                const uint32_t st = base + s * CH_STAGE_BYTES;
+                const float* whi = c.W + (size_t)l * 2 * HH;
+                const size_t ow = ((size_t)nb * KB + k0 + kb) * SDF_TILE_FLOATS;
+                tma_bulk_g2s(st + 2 * SDF_TILE_BYTES, whi + ow, SDF_TILE_BYTES, full);
+                tma_bulk_g2s(st + 3 * SDF_TILE_BYTES, whi + HH + ow, SDF_TILE_BYTES, full);
+            };
+            const int npre = kbs < CH_STAGES ? kbs : CH_STAGES;
+            uint32_t it = 0;
+            for (int l = 0; l < nl; l++) {
+                const float* xhi = c.act[l & 1][0];
+                const float* xlo = c.act[l & 1][1];
+                for (int mb = 0; mb < row_blocks; mb++) {
+                    const bool first = (mb == 0 && l > 0);
+                    if (first) {
+                        for (int j = 0; j < npre; j++) issue_w(l, j, it + (uint32_t)j);      // independent of the activations
+                        const unsigned need = (unsigned)l * nctas;                            // layer l - 1 is complete device-wide
+                        unsigned seen;
+                        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(c.sync) : "memory"); } while (seen < need);
+                        asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes of the other CTAs before this CTA's bulk copies
+                    }
+                    for (int kb = 0; kb < kbs; kb++, it++) {
+                        if (!(first && kb < npre)) issue_w(l, kb, it);
+                        const uint32_t s = it % CH_STAGES;
+                        const uint32_t full = BAR_F + 8 * s;
+                        const uint32_t st = base + s * CH_STAGE_BYTES;
+                        const size_t oa = ((size_t)mb * KB + k0 + kb) * SDF_TILE_FLOATS;
+                        tma_bulk_g2s(st, xhi + oa, SDF_TILE_BYTES, full);
+                        tma_bulk_g2s(st + SDF_TILE_BYTES, xlo + oa, SDF_TILE_BYTES, full);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            int tile = 0;
+            for (int l = 0; l < nl; l++) {
+                for (int mb = 0; mb < row_blocks; mb++, tile++) {
+                    if (tile > 0) {                                      // the epilogue has drained the accumulator of the previous tile
+                        mbar_wait(BAR_SD, (uint32_t)(tile - 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    for (int kb = 0; kb < kbs; kb++, it++) {
+                        const uint32_t s = it % CH_STAGES, ph = (it / CH_STAGES) & 1;
+                        mbar_wait(BAR_F + 8 * s, ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t as = base + s * CH_STAGE_BYTES, ws = as + 2 * SDF_TILE_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < SDF_BK / 8; ks++) {
+                            const uint32_t ko = ks * 256;
+                            const uint64_t ahi = umma_desc(as + ko), alo = umma_desc(as + SDF_TILE_BYTES + ko);
+                            const uint64_t bhi = umma_desc(ws + ko), blo = umma_desc(ws + SDF_TILE_BYTES + ko);
+                            umma_tf32(tmem_acc, alo, bhi, idesc, (kb | ks) ? 1u : 0u);
+                            umma_tf32(tmem_acc, ahi, blo, idesc, 1u);
+                            umma_tf32(tmem_acc, ahi, bhi, idesc, 1u);
+                        }
+                        umma_commit(BAR_E + 8 * s);
+                    }
+                    umma_commit(BAR_TF);
+                }
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int rl = 32 * q + lane;                               // row inside the 128-row block = TMEM lane
+        const int et = threadIdx.x - 64;                            // 0..127 among the epilogue threads
+        const size_t row_off = (size_t)(rl >> 3) * 256 + (rl & 7) * 4;
+        const int col0 = nb * CH_BN + 16 * (int)rank;               // the 16 output columns this CTA finishes
+        const size_t out_off = (size_t)(col0 / SDF_BK) * SDF_TILE_FLOATS + (size_t)((col0 % SDF_BK) / 4) * 32 + row_off;
+        int tile = 0;
+        for (int l = 0; l < nl; l++) {
+            float bv[16];
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(c.bias + (size_t)l * H + col0 + 4 * g));
+                bv[4 * g] = b4.x; bv[4 * g + 1] = b4.y; bv[4 * g + 2] = b4.z; bv[4 * g + 3] = b4.w;
+            }
+            float* yhi = c.act[(l + 1) & 1][0];
+            float* ylo = c.act[(l + 1) & 1][1];
+            for (int mb = 0; mb < row_blocks; mb++, tile++) {
+                const uint32_t par = (uint32_t)tile & 1;
+                mbar_wait(BAR_TF, par);                                 // every MMA of this tile has retired: the accumulator is complete
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int cc = 0; cc < CH_BN; cc += 32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)cc, v);
+#pragma unroll
+                    for (int c4 = 0; c4 < 8; c4++)                      // staging[column / 4][row][4]: consecutive lanes -> consecutive 16-byte words
+                        st_smem_f4(stg_sm + (uint32_t)(((cc >> 2) + c4) * SDF_BM + rl) * 16u, __uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]),
+                                   __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et < SK_SPLIT) mbar_arrive_remote(mapa_u32(BAR_RDY, (uint32_t)et));
+                if (lane == 0) mbar_arrive(BAR_SD);                     // TMEM has been read: the next tile's MMAs may overwrite it
+                mbar_wait_cluster(BAR_RDY, par);                        // all 8 partial tiles are in shared memory
+                float acc[16];
+#pragma unroll
+                for (int e = 0; e < 16; e++) acc[e] = 0.f;
+#pragma unroll
+                for (uint32_t r = 0; r < SK_SPLIT; r++) {               // fixed order: deterministic
+                    const uint32_t ra = mapa_u32(stg_sm + (uint32_t)((4 * rank) * SDF_BM + rl) * 16u, r);
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const float4 a = ld_dsmem_f4(ra + (uint32_t)g * SDF_BM * 16u);
+                        acc[4 * g] += a.x; acc[4 * g + 1] += a.y; acc[4 * g + 2] += a.z; acc[4 * g + 3] += a.w;
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");          // all reads of the peers' tiles are done
+                if (et < SK_SPLIT) mbar_arrive_remote(mapa_u32(BAR_FREE, (uint32_t)et));
+                float* dh = yhi + (size_t)mb * KB * SDF_TILE_FLOATS + out_off;
+                float* dl = ylo + (size_t)mb * KB * SDF_TILE_FLOATS + out_off;
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    float h[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const float y = fmaxf(acc[4 * g + e] + bv[4 * g + e], 0.f);
+                        h[e] = tf32_hi(y); lo[e] = y - h[e];
+                    }
+                    *reinterpret_cast<float4*>(dh + 32 * g) = make_float4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<float4*>(dl + 32 * g) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+                mbar_wait_cluster(BAR_FREE, par);                       // no peer still reads this CTA's partial tile: it may be overwritten
+            }
+            if (l + 1 < nl) {
+                // device-wide barrier, arrive side: this CTA's share of the layer's activations is written and visible
+                __threadfence();
+                asm volatile("fence.proxy.async;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (et == 0) {
+                    __threadfence();
+                    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(c.sync), "r"(1u) : "memory");
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)CH_TMEM_COLS) : "memory");
+    }
+    if (threadIdx.x == 0) {
+        // every CTA has passed its last barrier wait before it gets here: the last one out re-arms the counters
+        const unsigned old = atomicAdd(c.sync + 1, 1u);
+        if (old == nctas - 1) { c.sync[0] = 0u; c.sync[1] = 0u; __threadfence(); }
+    }
+}
+
 // ---------------------------------------------------------------- weights
 // weight_norm (deepsdf.py:3): W[o, :] = g[o] * v[o, :] / ||v[o, :]||.  One block per output row; writes the
 // plain fp32 row (first / last layer) and/or the hi / lo UMMA tiles (hidden layers).

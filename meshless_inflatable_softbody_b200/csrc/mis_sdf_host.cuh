@@ -2,6 +2,7 @@
 // tiles of one network and enqueues the layer chain of mis_sdf.cuh.
 #pragma once
 #include "mis_sdf.cuh"
+#include <stdlib.h>
 #include <string>
 #include <vector>
 
@@ -10,7 +11,12 @@ struct MisSdf {
     int H = 0;                 // hidden width (network_size = 1024)
     int cap = 0;               // activation capacity in rows (multiple of 128)
     float *W0 = nullptr, *b0 = nullptr;              // first layer, plain [H,3], [H]
-    std::vector<float*> Whi, Wlo, bh;                // hidden layers: UMMA tiles [H,H] hi / lo, bias [H]
+    std::vector<float*> Whi, Wlo, bh;                // hidden layers: UMMA tiles [H,H] hi / lo (both inside Wslab, hi then lo per layer), bias [H]
+    float* Wslab = nullptr;                          // all hidden-layer weights, contiguous: one L2 access-policy window per layer
+    float* bslab = nullptr;                          // hidden-layer biases, contiguous [L-2][H] (bh[l] point into it)
+    unsigned* chain_sync = nullptr;                  // device-wide barrier / exit counters of k_sdf_chain_sk
+    int chain_mode = 1;                              // 1: few-row queries run all hidden layers in one cooperative launch (MIS_SDF_CHAIN=0: one launch per layer)
+    bool l2_pin = false;                             // per-step contact query: keep the weights in the persisting part of L2
     float *wl = nullptr, *bl = nullptr;              // last layer, plain [H], [1]
     float *act[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // ping-pong activations, [buf][hi/lo], cap x H tiled
     float *vals = nullptr;     // 4 x cap scalars: sdf at p, p+eps ex, p+eps ey, p+eps ez
@@ -23,24 +29,40 @@ struct MisSdf {
 namespace mis {
 
 // kernel launch, optionally as a programmatic dependent launch of the previous kernel in the stream (see pdl_wait / pdl_trigger)
+// pin: optional [base, bytes) range this launch keeps in the persisting part of L2 (everything else it touches streams)
+struct L2Pin { const void* base = nullptr; size_t bytes = 0; };
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+inline cudaError_t launch_kp(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, L2Pin pin, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (pdl) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
+    if (pin.base && pin.bytes) {
+        at[na].id = cudaLaunchAttributeAccessPolicyWindow;
+        at[na].val.accessPolicyWindow.base_ptr = const_cast<void*>(pin.base);
+        at[na].val.accessPolicyWindow.num_bytes = pin.bytes;
+        at[na].val.accessPolicyWindow.hitRatio = 1.f;
+        at[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        at[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        na++;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    return launch_kp(kern, grid, block, smem, st, pdl, L2Pin{}, args...);
 }
 
 inline void sdf_free(MisSdf* s) {
     if (!s) return;
-    void* ptrs[] = {s->W0, s->b0, s->wl, s->bl, s->act[0][0], s->act[0][1], s->act[1][0], s->act[1][1], s->vals};
+    void* ptrs[] = {s->W0, s->b0, s->wl, s->bl, s->act[0][0], s->act[0][1], s->act[1][0], s->act[1][1], s->vals, s->Wslab, s->bslab, s->chain_sync};
     for (void* p : ptrs) if (p) cudaFree(p);
-    for (float* p : s->Whi) if (p) cudaFree(p);
-    for (float* p : s->Wlo) if (p) cudaFree(p);
-    for (float* p : s->bh) if (p) cudaFree(p);
     delete s;
 }
 
@@ -72,7 +94,9 @@ inline cudaError_t sdf_forward(MisSdf* s, const float* pts, const int* idx, int 
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_sdf_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sdf_gemm_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sdf_chain_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES);
         if (e != cudaSuccess) return e;
+        { const char* c = getenv("MIS_SK_CARVEOUT"); if (c && c[0]) cudaFuncSetAttribute(k_sdf_gemm_sk, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c)); }
         attr_set = true;
     }
     const int m_pad = (rows + 127) / 128 * 128;
@@ -86,11 +110,30 @@ inline cudaError_t sdf_forward(MisSdf* s, const float* pts, const int* idx, int 
     s->launches++;
     // few rows (a device-side count = the per-step contact query, or a small host-side count): split-K over 8-CTA clusters;
     // bulk queries: persistent 128 x 256 tiles
-    const bool skinny = s->force_path ? (s->force_path == 1) : (H <= SK_MAX_KBS * SK_SPLIT * SDF_BK && (m_count != nullptr || rows <= 1024));
+    const bool skinny = s->force_path ? (s->force_path == 1 || s->force_path == 3) : (H <= SK_MAX_KBS * SK_SPLIT * SDF_BK && (m_count != nullptr || rows <= 1024));
     int cur = 0;
-    for (size_t l = 0; l < s->Whi.size(); l++) {
+    // the cooperative launch takes at most 15 co-resident 8-CTA clusters on a B200 (cudaOccupancyMaxActiveClusters): H <= 15 * 128
+    const bool chain = skinny && s->chain_mode && s->force_path != 1 && !s->Whi.empty() && H % CH_BN == 0 && H / CH_BN <= 15;
+    if (chain) {
+        // every hidden layer in one cooperative launch (all CTAs co-resident: they meet at a device-wide barrier per layer)
+        SkChain c;
+        c.W = s->Wslab; c.bias = s->bslab; c.n_layers = (int)s->Whi.size(); c.sync = s->chain_sync;
+        for (int b = 0; b < 2; b++) for (int h = 0; h < 2; h++) c.act[b][h] = s->act[b][h];
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((H / CH_BN) * SK_SPLIT); cfg.blockDim = dim3(SDF_THREADS); cfg.dynamicSmemBytes = CH_SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        le = cudaLaunchKernelEx(&cfg, k_sdf_chain_sk, c, H, rows, m_count);
+        if (le != cudaSuccess) return le;
+        s->launches++; s->gemm_launches++;
+        cur = c.n_layers & 1;
+    }
+    for (size_t l = 0; l < s->Whi.size() && !chain; l++) {
         if (skinny) {
-            le = launch_k(k_sdf_gemm_sk, dim3((H / SK_BN) * SK_SPLIT), dim3(SDF_THREADS), SK_SMEM_BYTES, st, true,
+            L2Pin pin;
+            if (s->l2_pin && m_count) { pin.base = s->Whi[l]; pin.bytes = 2 * (size_t)H * H * sizeof(float); }
+            le = launch_kp(k_sdf_gemm_sk, dim3((H / SK_BN) * SK_SPLIT), dim3(SDF_THREADS), SK_SMEM_BYTES, st, true, pin,
                           (const float*)s->act[cur][0], (const float*)s->act[cur][1], (const float*)s->Whi[l], (const float*)s->Wlo[l], (const float*)s->bh[l],
                           H, H, s->act[cur ^ 1][0], s->act[cur ^ 1][1], rows, m_count);
             if (le != cudaSuccess) return le;
@@ -105,7 +148,7 @@ inline cudaError_t sdf_forward(MisSdf* s, const float* pts, const int* idx, int 
     if (final_buf) *final_buf = cur;
     if (out) {
         const int blocksl = (rows + 7) / 8;
-        le = launch_k(k_sdf_last, dim3(blocksl < 148 * 8 ? blocksl : 148 * 8), dim3(256), 0, st, skinny,
+        le = launch_k(k_sdf_last, dim3(blocksl < 148 * 8 ? blocksl : 148 * 8), dim3(256), 0, st, skinny && !chain,
                       (const float*)s->act[cur][0], (const float*)s->act[cur][1], rows, m_count, (const float*)s->wl, (const float*)s->bl, H, out);
         if (le != cudaSuccess) return le;
         s->launches++;

@@ -101,7 +101,8 @@ class DeepSDF:
         return x
 
     def set_gemm_path(self, path: int) -> None:
-        """0 = automatic, 1 = split-K cluster kernel (few rows), 2 = persistent big-tile kernel (bulk)."""
+        """0 = automatic, 1 = split-K cluster kernel, one launch per layer, 2 = persistent big-tile kernel (bulk),
+        3 = split-K cluster kernel, all hidden layers in one cooperative launch (few rows: per-step contact)."""
         native.check(self.L.mis_sdf_set_gemm_path(self._h, int(path)), "mis_sdf_set_gemm_path")
 
     def profile_gemm(self, m: int, reps: int = 10) -> float:

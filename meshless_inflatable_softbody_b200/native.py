@@ -103,6 +103,16 @@ SYMBOLS = {
     "mis_profile_step": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mis_gather_next_positions": (C.c_int, [_vp, _ip, C.c_int, _fp, _vp]),
     "mis_scatter_next_positions": (C.c_int, [_vp, _ip, C.c_int, _fp, _vp]),
+    "mis_set_volumes": (C.c_int, [_vp, _ip, C.c_int, _fp, _vp]),
+    "mis_export_slots": (C.c_int, [_vp, _ip, C.c_int, _ip, _vp]),
+    "mis_halo_ipc_handles": (C.c_int, [_vp, C.c_char_p]),
+    "mis_halo_local_ptrs": (C.c_int, [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "mis_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mis_ipc_close": (C.c_int, [_vp]),
+    "mis_halo_connect": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                   C.c_int, _ip, _ip, _ip, C.c_int, _ip, _vp]),
+    "mis_halo_disconnect": (C.c_int, [_vp]),
+    "mis_halo_status": (C.c_int, [_vp, _vp, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
     "mis_sdf_create": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_void_p), _vp, C.POINTER(C.c_void_p)]),
     "mis_sdf_destroy": (C.c_int, [_vp]),

@@ -176,6 +176,58 @@ class Simulator:
                      "mis_scatter_next_positions")
         torch.cuda.current_stream(self.device).wait_stream(self.stream)     # keeps `x` alive until the scatter has read it
 
+    def volumes(self) -> torch.Tensor:
+        """V_i = m_i / rho_i (compute_v_i, sim.py:154-167), caller order."""
+        return self.fields(("vol",))["vol"]
+
+    def set_volumes(self, ids: torch.Tensor, vol: torch.Tensor):
+        """Overwrite V of the particles `ids` (int32 caller ids) -- ghosts of a slab partition take their owner's value."""
+        ids = ids.to(device=self.device, dtype=torch.int32).contiguous()
+        vol = vol.to(device=self.device, dtype=torch.float32).contiguous()
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        native.check(self.L.mis_set_volumes(self._h, ids.data_ptr(), int(ids.numel()), vol.data_ptr(), self._st()), "mis_set_volumes")
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+    def slots_of(self, ids: torch.Tensor) -> torch.Tensor:
+        """Cell-sorted slot of each caller id (the address a peer pushes a ghost's position to)."""
+        ids = ids.to(device=self.device, dtype=torch.int32).contiguous()
+        out = torch.empty(int(ids.numel()), device=self.device, dtype=torch.int32)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        native.check(self.L.mis_export_slots(self._h, ids.data_ptr(), int(ids.numel()), out.data_ptr(), self._st()), "mis_export_slots")
+        self.stream.synchronize()
+        return out
+
+    def halo_ipc_handles(self) -> bytes:
+        buf = C.create_string_buffer(192)
+        native.check(self.L.mis_halo_ipc_handles(self._h, buf), "mis_halo_ipc_handles")
+        return bytes(buf.raw)
+
+    def halo_local_ptrs(self):
+        a, b, f = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        native.check(self.L.mis_halo_local_ptrs(self._h, C.byref(a), C.byref(b), C.byref(f)), "mis_halo_local_ptrs")
+        return int(a.value), int(b.value), int(f.value)
+
+    def halo_connect(self, peer_xv0, peer_xv1, peer_flag, push_ids, push_peer, push_slot, ghost_ids):
+        """Switch on the fused halo push (include/mis.h, mis_halo_connect).  Pointer lists are ints (device addresses
+        valid in this process); push_* / ghost_ids are int32 arrays."""
+        k = len(peer_xv0)
+        arr = lambda v: (C.c_void_p * max(1, k))(*[C.c_void_p(int(x)) for x in v])
+        dev = lambda a: torch.as_tensor(np.ascontiguousarray(np.asarray(a, np.int32)), device=self.device)
+        pid, pp, ps, gid = dev(push_ids), dev(push_peer), dev(push_slot), dev(ghost_ids)
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        native.check(self.L.mis_halo_connect(self._h, k, arr(peer_xv0), arr(peer_xv1), arr(peer_flag),
+                                             int(pid.numel()), pid.data_ptr(), pp.data_ptr(), ps.data_ptr(),
+                                             int(gid.numel()), gid.data_ptr(), self._st()), "mis_halo_connect")
+
+    def halo_disconnect(self):
+        native.check(self.L.mis_halo_disconnect(self._h), "mis_halo_disconnect")
+
+    def halo_status(self):
+        """(timed_out, exchanges): synchronises the stream."""
+        e, x = C.c_int(0), C.c_longlong(0)
+        native.check(self.L.mis_halo_status(self._h, self._st(), C.byref(e), C.byref(x)), "mis_halo_status")
+        return bool(e.value), int(x.value)
+
     # ------------------------------------------------------------------ obstacle contact (extension)
     def set_sdf_obstacle(self, sdf, bbox_model, xform=None, fd_eps: float = 1e-3):
         """Per-step contact against a DeepSDF-encoded obstacle (extension; the reference evaluates its SDF once,

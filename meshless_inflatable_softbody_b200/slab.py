@@ -14,6 +14,15 @@ sets and the send/receive index lists are STATIC for the whole run:
 
 There is no global reduction in the physics (the reference has no pressure / enclosed-volume term).
 
+Two exchange mechanisms:
+  * halo="p2p" (default when every rank is on one NVLink box): the fused halo push of include/mis.h -- the force
+    kernel's part_1 epilogue stores a boundary particle's new position straight into the peers' ghost slots over
+    NVLink peer memory, a one-block kernel publishes / awaits an epoch flag, and step(n) is CUDA-graph chunks with no
+    host, NCCL or copy kernel in the loop;
+  * halo="nccl": gather -> batch_isend_irecv -> scatter after every step (works across nodes; the baseline).
+Volumes V_i = m_i / rho_i (compute_v_i, sim.py:154-167) are static and need a particle's whole neighbourhood, which an
+outer ghost lacks locally: owners send them once after set_mass.
+
 Host logic only (numpy + torch.distributed point-to-point); the particle arithmetic stays in the CUDA library.
 """
 from __future__ import annotations
@@ -133,9 +142,62 @@ def exchange_halo(plan: RankPlan, gather, scatter, dist=None, group=None, device
         scatter(ids, recv_bufs[q])
 
 
+def plan_push(plan: RankPlan, peers: List[int], peer_recv_slots: Dict[int, np.ndarray]):
+    """(ids, peer index, remote slot) triples of the fused halo push.  The k-th entry of plan.send[q] and the k-th entry
+    of rank q's recv[plan.rank] are the same particle (both ordered by global id); peer_recv_slots[q][k] is the slot rank q
+    keeps that ghost in.  `peers` fixes the peer indices (position in the list)."""
+    ids, pidx, slots = [], [], []
+    for q, local in sorted(plan.send.items()):
+        sl = np.asarray(peer_recv_slots[q]).reshape(-1)
+        if len(sl) != len(local):
+            raise ValueError(f"rank {plan.rank} sends {len(local)} particles to {q}, which expects {len(sl)}")
+        ids.append(np.asarray(local)); pidx.append(np.full(len(local), peers.index(q))); slots.append(sl)
+    cat = lambda v: np.concatenate(v).astype(np.int32) if v else np.zeros(0, np.int32)
+    return cat(ids), cat(pidx), cat(slots)
+
+
+def peers_of(plan: RankPlan) -> List[int]:
+    return sorted(set(plan.send) | set(plan.recv))
+
+
+def exchange_volumes_in_process(sims):
+    """Owners' volumes -> ghosts, all ranks in one process."""
+    vols = {s.rank: s.sim.volumes() for s in sims}
+    for s in sims:
+        ids, vals = [], []
+        for q, rid in s._recv.items():
+            ids.append(rid); vals.append(vols[q][sims[q]._send[s.rank].long()].to(s.device))
+        if ids:
+            import torch
+            s.sim.set_volumes(torch.cat(ids), torch.cat(vals))
+
+
+def connect_in_process(sims):
+    """Fused halo push between ranks that live in ONE process (tests): raw device pointers instead of IPC handles."""
+    ptrs = {s.rank: s.sim.halo_local_ptrs() for s in sims}
+    recv_slots = {s.rank: {q: s.sim.slots_of(ids).cpu().numpy() for q, ids in s._recv.items()} for s in sims}
+    peer_lists = {s.rank: peers_of(s.plan) for s in sims}
+    for s in sims:
+        peers = peer_lists[s.rank]
+        ids, pidx, slots = plan_push(s.plan, peers, {q: recv_slots[q][s.rank] for q in s.plan.send})
+        flag = [ptrs[q][2] + 4 * peer_lists[q].index(s.rank) for q in peers]
+        s.sim.halo_connect([ptrs[q][0] for q in peers], [ptrs[q][1] for q in peers], flag, ids, pidx, slots,
+                           np.arange(s.n_owned, s.sim.n, dtype=np.int32))
+        s.halo = "p2p"
+    for s in sims:
+        s.sim.synchronize()
+
+
 def step_in_process(sims, n_steps: int = 1):
     """All ranks of a partition driven from ONE process (tests, single-GPU debugging): the same per-step sequence as
     SlabSimulator.step, with the point-to-point exchange replaced by device-to-device copies."""
+    if sims and sims[0].halo == "p2p":
+        # the pushes and flag waits are inside each rank's step graph; the ranks' streams run side by side
+        for s in sims:
+            s.sim.step(int(n_steps))
+            s.frame += int(n_steps)
+        return
+
     def exchange():
         bufs = {}
         for s in sims:
@@ -161,7 +223,8 @@ class SlabSimulator:
     per-step halo exchange.  Method names follow Simulator / the reference's control functions."""
 
     def __init__(self, x0_global, config=None, rank: int = 0, world_size: int = 1, device: str = "cuda:0",
-                 group=None, partition: Optional[SlabPartition] = None, in_process: bool = False, **sim_kw):
+                 group=None, partition: Optional[SlabPartition] = None, in_process: bool = False, halo: str = "auto",
+                 **sim_kw):
         import torch
         import torch.distributed as dist
         from .config import SceneConfig
@@ -185,10 +248,67 @@ class SlabSimulator:
         self._recv = {q: torch.as_tensor(ids, dtype=torch.int32, device=self.device) for q, ids in self.plan.recv.items()}
         self.frame = 0
         self.exchanges = 0
+        self.halo = "nccl"
+        self._mapped = []
+        if world_size > 1 and not in_process:
+            self._exchange_volumes()
+            if halo == "auto":
+                import os
+                local = int(os.environ.get("LOCAL_WORLD_SIZE", world_size))
+                halo = "p2p" if local == world_size else "nccl"
+            if halo == "p2p":
+                self._connect_p2p()
+            elif halo != "nccl":
+                raise ValueError("halo must be 'auto', 'p2p' or 'nccl'")
 
     # halo plumbing -----------------------------------------------------------------------------------------
+    def _exchange_volumes(self):
+        """Owners' V_i -> ghosts (once per set_mass): point-to-point, same lists as the position exchange."""
+        import torch
+        vol = self.sim.volumes()
+        ops, bufs = [], {}
+        for q, ids in sorted(self._recv.items()):
+            bufs[q] = torch.empty(len(ids), dtype=torch.float32, device=self.device)
+            ops.append(self.dist.P2POp(self.dist.irecv, bufs[q], q, group=self.group))
+        keep = []
+        for q, ids in sorted(self._send.items()):
+            keep.append(vol[ids.long()].contiguous())
+            ops.append(self.dist.P2POp(self.dist.isend, keep[-1], q, group=self.group))
+        if ops:
+            for w in self.dist.batch_isend_irecv(ops):
+                w.wait()
+            torch.cuda.synchronize(self.device)
+        if bufs:
+            qs = sorted(bufs)
+            self.sim.set_volumes(torch.cat([self._recv[q] for q in qs]), torch.cat([bufs[q] for q in qs]))
+
+    def _connect_p2p(self):
+        """Exchange CUDA IPC handles of the position buffers / flag arrays and the ghosts' slots, map the peers' memory,
+        and hand the push table to the library (mis_halo_connect)."""
+        import ctypes as C
+        from . import native
+        sim = self.sim
+        peers = peers_of(self.plan)
+        mine = {"handles": sim.halo_ipc_handles(), "peers": peers,
+                "recv_slots": {q: sim.slots_of(ids).cpu().numpy() for q, ids in self._recv.items()}}
+        everyone = [None] * self.world
+        self.dist.all_gather_object(everyone, mine, group=self.group)
+        xv0, xv1, flag = [], [], []
+        for q in peers:
+            h = everyone[q]["handles"]
+            ptr = []
+            for k in range(3):
+                p = C.c_void_p()
+                native.check(sim.L.mis_ipc_open(h[64 * k: 64 * k + 64], C.byref(p)), "mis_ipc_open")
+                ptr.append(int(p.value)); self._mapped.append(int(p.value))
+            xv0.append(ptr[0]); xv1.append(ptr[1])
+            flag.append(ptr[2] + 4 * everyone[q]["peers"].index(self.rank))
+        ids, pidx, slots = plan_push(self.plan, peers, {q: everyone[q]["recv_slots"][self.rank] for q in self.plan.send})
+        sim.halo_connect(xv0, xv1, flag, ids, pidx, slots, np.arange(self.n_owned, sim.n, dtype=np.int32))
+        self.halo = "p2p"
+
     def _exchange(self):
-        if self.world == 1 or self.in_process:
+        if self.world == 1 or self.in_process or self.halo == "p2p":
             return
         import torch
         sim = self.sim
@@ -198,13 +318,26 @@ class SlabSimulator:
         self.exchanges += 1
 
     # control functions ---------------------------------------------------------------------------------------
+    def set_mass(self, m):
+        self.sim.set_mass(m)
+        if self.world > 1 and not self.in_process:
+            self._exchange_volumes()
+
     def startup(self, v0=None):
+        if self.halo == "p2p" and self.world > 1 and not self.in_process:
+            self.sim.synchronize()
+            self.dist.barrier(group=self.group)       # every rank's set-up kernels are done before the first push
         self.sim.startup(v0)
         self.sim.step(0)          # frame-0 force evaluation + part_1 (sim.py:349-353) so that x(1) exists
         self._exchange()
         self.frame = 0
 
     def step(self, n_steps: int = 1):
+        if self.halo == "p2p":
+            self.sim.step(int(n_steps))               # pushes + flag waits are inside the step graph
+            self.exchanges += int(n_steps)
+            self.frame += int(n_steps)
+            return
         for _ in range(int(n_steps)):
             self.sim.step(1)
             self._exchange()
@@ -241,5 +374,16 @@ class SlabSimulator:
             X[idx] = buf[:c, :3]; V[idx] = buf[:c, 3:]
         return X, V
 
+    def halo_ok(self) -> bool:
+        """False if a flag wait of the fused push timed out (a peer died or the ranks' call sequences diverged)."""
+        return not self.sim.halo_status()[0]
+
     def close(self):
+        if self._mapped:
+            self.sim.synchronize()
+            self.dist.barrier(group=self.group)       # nobody is still pushing into memory about to be unmapped
+            self.sim.halo_disconnect()
+            for p in self._mapped:
+                self.sim.L.mis_ipc_close(p)
+            self._mapped = []
         self.sim.close()

@@ -50,10 +50,12 @@ def test_ragged_sizes_against_oracle(seeded, n):
     assert np.abs(got[sub] - want).max() <= 4e-6 * np.abs(want).max() + 1e-7
 
 
-@pytest.mark.parametrize("path,n", [(1, 1), (1, 129), (1, 1000), (1, 1024 + 77), (1, 3000), (2, 1), (2, 129), (2, 1000)])
+@pytest.mark.parametrize("path,n", [(1, 1), (1, 129), (1, 1000), (1, 1024 + 77), (1, 3000), (2, 1), (2, 129), (2, 1000),
+                                    (3, 1), (3, 129), (3, 300), (3, 1000), (3, 3000)])
 def test_both_hidden_layer_kernels_at_any_row_count(seeded, path, n):
-    """The split-K cluster kernel (few rows: per-step contact) and the persistent big-tile kernel (bulk) are both correct for
-    any row count; 3000 rows = 24 row-blocks = 3 TMEM groups of the split-K kernel."""
+    """The split-K cluster kernels (few rows: per-step contact; 1 = one launch per layer, 3 = every hidden layer in one cooperative
+    launch with a device-wide barrier between layers) and the persistent big-tile kernel (bulk) are all correct for any row count,
+    agree bit for bit where they share the reduction order (1 vs 3), and are bit-reproducible."""
     st, net = seeded
     rng = np.random.default_rng(100 + n)
     p = rng.uniform(-1.0, 1.0, size=(n, 3)).astype(np.float32)
@@ -68,6 +70,13 @@ def test_both_hidden_layer_kernels_at_any_row_count(seeded, path, n):
     assert np.isfinite(got).all()
     assert np.abs(got[sub] - want).max() <= 4e-6 * np.abs(want).max() + 1e-7
     assert np.array_equal(got, again)                       # fixed reduction order: bit-reproducible
+    if path == 3:
+        net.set_gemm_path(1)
+        try:
+            per_layer = net(p).cpu().numpy()[:, 0]
+        finally:
+            net.set_gemm_path(0)
+        assert np.array_equal(got, per_layer)               # same K split, same fixed-order reduction
 
 
 def test_small_network_and_octahedron_exactness():

@@ -9,7 +9,8 @@ import torch
 
 from conftest import make_oracle
 from meshless_inflatable_softbody_b200 import SceneConfig, scenes
-from meshless_inflatable_softbody_b200.slab import SlabPartition, SlabSimulator, step_in_process
+from meshless_inflatable_softbody_b200.slab import (SlabPartition, SlabSimulator, step_in_process, connect_in_process,
+                                                    exchange_volumes_in_process)
 
 pytestmark = pytest.mark.gpu
 FLOOR_MULT = 4.0
@@ -22,14 +23,21 @@ def _beam(n=9000):
     return scenes.jittered_ellipsoid(n, seed=0, aspect=(4.0, 1.0, 1.0), low_drop=True)
 
 
+@pytest.mark.parametrize("halo", ["copy", "p2p"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_partitioned_run_matches_single_domain(world):
+def test_partitioned_run_matches_single_domain(world, halo):
+    """halo = "copy": gather / device copy / scatter after every step (the NCCL path's data flow);
+    halo = "p2p": the fused push -- positions stored into the peers' ghost slots by the force kernel's epilogue, epoch
+    flags instead of host-driven exchanges, steps in CUDA-graph chunks."""
     from meshless_inflatable_softbody_b200 import Simulator
     cfg = SceneConfig()
     x0 = _beam()
     steps = 80
     part = SlabPartition.build(x0, cfg.h, world)
     sims = [SlabSimulator(x0, cfg, rank=r, world_size=world, partition=part, in_process=True) for r in range(world)]
+    exchange_volumes_in_process(sims)
+    if halo == "p2p":
+        connect_in_process(sims)
     for s in sims:
         s.sim.startup(); s.sim.step(0)
     step_in_process(sims, 0)
@@ -52,30 +60,72 @@ def test_partitioned_run_matches_single_domain(world):
     assert np.abs(V - v1).max() <= FLOOR_MULT * fv + 2e-5, (np.abs(V - v1).max(), fv)
     assert np.abs(X - a.position()).max() <= FLOOR_MULT * fx + 4e-9
     assert V[:, 1].max() > -0.4 - 10.0 * steps * cfg.time_step + 0.01      # some particle is slower than free fall: ground contact acted
-    assert all(s.exchanges == steps + 1 for s in sims)
+    if halo == "p2p":
+        for s in sims:
+            timed_out, exchanges = s.sim.halo_status()
+            assert not timed_out and exchanges == steps + 1
+    else:
+        assert all(s.exchanges == steps + 1 for s in sims)
 
 
-def _nccl_worker(rank, world, x0, steps, port, out_dir):
+def test_ghost_volumes_and_strained_forces_match_single_domain():
+    """compute_v_i (sim.py:154-167) of an outer ghost lacks part of its neighbourhood locally; the owners' volumes are
+    exchanged once.  Checked where it matters: elastic forces of a strongly (20 %) stretched state, owned particles."""
+    from meshless_inflatable_softbody_b200 import Simulator
+    cfg = SceneConfig()
+    x0 = _beam()
+    world = 2
+    part = SlabPartition.build(x0, cfg.h, world)
+    sims = [SlabSimulator(x0, cfg, rank=r, world_size=world, partition=part, in_process=True) for r in range(world)]
+    one = Simulator(x0, cfg)
+    vol1 = one.volumes().cpu().numpy()
+    c = x0.mean(0)
+    xs = ((x0 - c) * np.array([1.2, 0.95, 0.9], np.float32) + c).astype(np.float32)
+    f1 = one.eval_forces(xs).cpu().numpy()
+    scale = np.abs(f1).max()
+    before = 0.0
+    for s in sims:
+        f = s.sim.eval_forces(xs[s.plan.local_ids]).cpu().numpy()[: s.n_owned]
+        before = max(before, np.abs(f - f1[s.plan.owned]).max())
+    exchange_volumes_in_process(sims)
+    after = 0.0
+    for s in sims:
+        v = s.sim.volumes().cpu().numpy()
+        layer1 = s.n_owned + np.nonzero(s.plan.ghost_layer == 1)[0]
+        assert np.array_equal(v[s.n_owned:], vol1[s.plan.ghosts])            # ghosts carry their owner's value, bit for bit
+        assert np.allclose(v[: s.n_owned], vol1[s.plan.owned], rtol=2e-6)     # owned: same sum, local summation order
+        assert len(layer1) > 0
+        f = s.sim.eval_forces(xs[s.plan.local_ids]).cpu().numpy()[: s.n_owned]
+        after = max(after, np.abs(f - f1[s.plan.owned]).max())
+    assert after <= 2e-5 * scale, (after, scale)
+    assert before > 100 * after, (before, after)      # without the exchange the boundary forces are visibly wrong
+
+
+def _nccl_worker(rank, world, x0, steps, port, out_dir, halo):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
-    sim = SlabSimulator(x0, SceneConfig(), rank=rank, world_size=world, device=f"cuda:{rank}")
+    sim = SlabSimulator(x0, SceneConfig(), rank=rank, world_size=world, device=f"cuda:{rank}", halo=halo)
+    assert sim.halo == halo
     sim.startup(); sim.step(steps)
+    assert sim.halo_ok()
     X, V = sim.gather_global()
     if rank == 0:
         np.save(os.path.join(out_dir, "X.npy"), X.cpu().numpy()); np.save(os.path.join(out_dir, "V.npy"), V.cpu().numpy())
     dist.barrier()
+    sim.close()
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("halo", ["nccl", "p2p"])
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_nccl_halo_exchange_two_gpus(tmp_path):
+def test_halo_exchange_two_gpus(tmp_path, halo):
     import torch.multiprocessing as mp
     from meshless_inflatable_softbody_b200 import Simulator
     x0 = _beam(12000)
     steps = 40
-    mp.spawn(_nccl_worker, args=(2, x0, steps, 29731, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_nccl_worker, args=(2, x0, steps, 29731 + (halo == "p2p"), str(tmp_path), halo), nprocs=2, join=True)
     X, V = np.load(tmp_path / "X.npy"), np.load(tmp_path / "V.npy")
     one = Simulator(x0, SceneConfig())
     one.startup(); one.step(steps)

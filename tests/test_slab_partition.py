@@ -119,3 +119,51 @@ def test_halo_exchange_matches_serial(world, tmp_path):
         got[np.load(tmp_path / f"ids_{r}.npy")] = np.load(tmp_path / f"x_{r}.npy")
     # owned particles see exactly the serial data flow; only ghost values are rounded to fp32 in transit
     assert np.abs(got - xs).max() < 5e-8
+
+
+# ---------------------------------------------------------------- fused halo push: the static push table
+def _push_worker(rank, world, x0, port, out_dir):
+    """Every rank keeps its local particles in a private, permuted slot order (a stand-in for the library's cell sort),
+    publishes the slots of its ghosts, builds the push triples with plan_push and 'pushes' by mailing (slot, value) pairs:
+    afterwards every ghost slot must hold the owner's value of exactly that particle."""
+    from meshless_inflatable_softbody_b200.slab import plan_push, peers_of
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    part = SlabPartition.build(x0, H, world)
+    plan = part.plans[rank]
+    local = plan.local_ids
+    rng = np.random.default_rng(100 + rank)
+    slot_of = rng.permutation(len(local))                    # local id -> slot
+    peers = peers_of(plan)
+    mine = {"peers": peers, "recv_slots": {q: slot_of[ids] for q, ids in plan.recv.items()}}
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine)
+    ids, pidx, slots = plan_push(plan, peers, {q: everyone[q]["recv_slots"][rank] for q in plan.send})
+    assert len(ids) == sum(len(v) for v in plan.send.values())
+    assert np.all(ids < plan.n_owned)                        # only owned particles are pushed
+    assert np.bincount(ids, minlength=1).max() <= 2          # at most two mirrors per particle (the kernel's table holds two)
+    value = local.astype(np.float64) * 10.0 + 1.0            # owner's value of a particle = f(global id)
+    mail = {q: [] for q in range(world)}
+    for i, p, s in zip(ids, pidx, slots):
+        mail[peers[p]].append((int(s), float(value[i])))
+    boxes = [None] * world
+    dist.all_gather_object(boxes, mail)
+    store = np.full(len(local), -1.0)
+    writes = np.zeros(len(local), np.int64)
+    for src in range(world):
+        for s, v in boxes[src][rank]:
+            store[s] = v; writes[s] += 1
+    ghost_slots = slot_of[plan.n_owned:]
+    assert np.all(writes[ghost_slots] == 1)                  # every ghost slot has exactly one writer
+    assert writes.sum() == len(plan.ghosts)                  # and nothing else is written
+    assert np.array_equal(store[ghost_slots], plan.ghosts.astype(np.float64) * 10.0 + 1.0)
+    np.save(os.path.join(out_dir, f"ok_{rank}.npy"), np.array([1]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_push_plan_fills_every_ghost_slot_once(world, tmp_path):
+    x0 = _beam(5000, seed=2)
+    port = 31500 + (os.getpid() % 2000) + world
+    mp.spawn(_push_worker, args=(world, x0, port, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok_{r}.npy").exists() for r in range(world))

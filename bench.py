@@ -11,7 +11,8 @@ Workloads
   N = 1 : BASELINE.json configs[1] -- ~100k-particle inflatable body (dense jittered sphere, reference defaults) dropped on
           a DeepSDF-encoded obstacle (the reference's 9 x 1024 architecture, deepsdf.py:12-38, with analytic octahedron
           weights) standing on the ground plane; contact = ground penalty (sim.py:238-244) + SDF penalty (extension).
-  N > 1 : one scene of N x (--n) particles (a beam, long axis x) slab-partitioned across the N GPUs with a per-step
+  N > 1 : one scene of N x (--n) particles (default 1.25 M per GPU: N = 8 is the 10M-particle scene of configs[4]; an
+          elongated body, long axis x) slab-partitioned across the N GPUs with a per-step
           halo exchange of the ghost particles' new positions (slab.py: fused P2P push over NVLink peer memory, or NCCL
           send/recv with --halo nccl); per-GPU work is fixed => "scaling": "weak".
           --mode batch runs independent scenes, one per GPU (configs[3]); --mode strong fixes the total particle count.
@@ -448,7 +449,8 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=100_000, help="particles per GPU")
+    ap.add_argument("--n", type=int, default=0, help="particles per GPU (default: 100 000 at N = 1 = configs[1]; 1 250 000 at N > 1, so that "
+                                                     "N = 8 is the 10M-particle scene of configs[4])")
     ap.add_argument("--n-total", type=int, default=10_000_000, help="total particles for --mode strong")
     ap.add_argument("--mode", default="slab", choices=["slab", "batch", "strong"], help="multi-GPU workload (N > 1)")
     ap.add_argument("--halo", default="auto", choices=["auto", "p2p", "nccl"], help="slab modes: ghost exchange mechanism")
@@ -460,6 +462,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.n <= 0:
+        args.n = 100_000 if int(os.environ.get("WORLD_SIZE", "1")) == 1 else 1_250_000
 
     from meshless_inflatable_softbody_b200 import SceneConfig
     cfg = SceneConfig()

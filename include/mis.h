@@ -174,6 +174,10 @@ int mis_halo_connect(MisSim* sim, int n_peers, void* const* peer_xv0, void* cons
                      int n_push, const int* push_ids_dev, const int* push_peer_dev, const int* push_slot_dev,
                      int n_ghost, const int* ghost_ids_dev, void* stream);
 int mis_halo_disconnect(MisSim* sim);
+/* wait = 0: the per-step kernel only publishes this rank's epoch and does NOT wait for the peers'; the caller orders the ranks
+ * itself (host synchronisation between steps).  For driving several ranks from one process on ONE GPU (tests), where kernels
+ * that wait on one another must not be used: nothing guarantees that they run at the same time.  Default 1.       */
+int mis_halo_set_wait(MisSim* sim, int wait);
 int mis_halo_status(MisSim* sim, void* stream, int* err, long long* exchanges);
 
 /* Per-particle fields of the current frame, caller order; any pointer may be NULL.

@@ -32,6 +32,7 @@ struct MisSim {
     MisParams p{};
     Consts c{};
     int G = 8, C = 2;                 // lanes per cluster, particles per cluster
+    bool pair_cells = true;           // MIS_PAIR_CELLS=0: keep the plain in-cell Morton order (A/B measurement)
     // caller-order copies
     float* x0_orig = nullptr;
     int* coords = nullptr;
@@ -97,6 +98,7 @@ struct MisSim {
     unsigned* halo_mem = nullptr;               // [0..MIS_MAX_PEERS) flags written by the peers, [MIS_MAX_PEERS] epoch, [MIS_MAX_PEERS + 1] error
     int halo_peers = 0;
     bool halo_on = false;
+    bool halo_wait = true;
     float4* peer_xv[2][MIS_MAX_PEERS] = {};
     unsigned* peer_flag[MIS_MAX_PEERS] = {};
     unsigned long long halo_timeout_ns = 20000000000ull;
@@ -196,6 +198,7 @@ extern "C" int mis_create(int n, const float* x0_dev, const MisParams* params, v
     int Cs = s->p.cluster_size ? s->p.cluster_size : 2;
     if (Cs != 1 && Cs != 2 && Cs != 4) { delete s; return fail(MIS_E_INVALID, "cluster_size must be 1, 2 or 4"); }
     s->C = Cs;
+    { const char* e = getenv("MIS_PAIR_CELLS"); if (e && e[0] == '0') s->pair_cells = false; }
     make_consts(s);
     s->d2_limit = find_d2_limit(s->p.h);
     const size_t N = (size_t)n;
@@ -346,6 +349,13 @@ extern "C" int mis_build_neighbors(MisSim* s, void* stream) {
     k_cell_table<<<nblk(n, 256), 256, 0, st>>>(s->keys, s->perm, s->coords, s->x0_orig, n, cmin, cdim, s->sub_bits,
                                                s->cell_start, s->cell_end, s->cell_lin_sorted, s->inv_perm, s->x0m);
     CK_LAUNCH(); s->launches++;
+    if (s->C > 1 && s->pair_cells) {
+        // close particles into the same cluster: greedy nearest-neighbour matching inside every cell (mis_neighbors.cuh)
+        k_pair_cells<<<nblk(s->ncells, 4), 128, 0, st>>>(s->x0m, s->cell_start, s->cell_end, s->ncells, s->perm, s->rs.vals_alt);
+        CK(cudaMemcpyAsync(s->perm, s->rs.vals_alt, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        k_apply_order<<<nblk(n, 256), 256, 0, st>>>(s->perm, s->x0_orig, n, s->inv_perm, s->x0m);
+        CK_LAUNCH(); s->launches += 2;
+    }
     CK(cudaMemsetAsync(s->max_k_dev, 0, sizeof(int), st));
     k_nbr_walk<<<nblk(n, 128), 128, 0, st>>>(s->x0m, s->cell_lin_sorted, s->cell_start, s->cell_end, cdim, n, s->d2_limit, 0,
                                              nullptr, nullptr, s->nbr_count, s->max_k_dev);
@@ -542,6 +552,7 @@ static void enqueue_halo_sync(MisSim* s, cudaStream_t st) {
     if (!s->halo_on) return;
     HaloSync h;
     h.n_peers = s->halo_peers;
+    h.wait = s->halo_wait ? 1 : 0;
     h.epoch = s->halo_mem + MIS_MAX_PEERS;
     h.my_flags = s->halo_mem;
     for (int p = 0; p < 4; p++) h.peer_flag[p] = s->peer_flag[p];
@@ -918,6 +929,13 @@ extern "C" int mis_halo_disconnect(MisSim* s) {
     drop_graph(s);
     s->halo_on = false; s->halo_peers = 0;
     s->dirty = true; s->forces_only = false;
+    return MIS_OK;
+}
+
+extern "C" int mis_halo_set_wait(MisSim* s, int wait) {
+    if (!s) return fail(MIS_E_INVALID, "null sim");
+    drop_graph(s);
+    s->halo_wait = wait != 0;
     return MIS_OK;
 }
 

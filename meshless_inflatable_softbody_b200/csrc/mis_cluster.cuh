@@ -80,6 +80,7 @@ __device__ __forceinline__ void store_next(const View& s, int i, float4 v) {
 // the flag.  A peer's pushes are visible here once its flag is (acquire).  Single block, thread p handles peer p.
 struct HaloSync {
     int n_peers;
+    int wait;                             // 0: publish only (the host orders the ranks)
     unsigned* epoch;                      // [0] exchanges done by this rank
     unsigned* my_flags;                   // [p] last epoch published by peer p (written remotely)
     unsigned* peer_flag[4];               // my entry in peer p's flag array (peer-mapped)
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(32) k_halo_sync(HaloSync h) {
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(h.peer_flag[threadIdx.x]), "r"(e) : "memory");
         const unsigned long long t0 = global_ns();
         const unsigned* f = h.my_flags + threadIdx.x;
-        for (;;) {
+        for (; h.wait;) {
             unsigned v;
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
             if ((int)(v - e) >= 0) break;

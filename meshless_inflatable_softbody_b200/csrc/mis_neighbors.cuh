@@ -98,6 +98,84 @@ __global__ void __launch_bounds__(256) k_cell_table(const uint32_t* __restrict__
     dst[0] = x0[3 * id]; dst[1] = x0[3 * id + 1]; dst[2] = x0[3 * id + 2];
 }
 
+// ---------------------------------------------------------------- in-cell pairing
+// The step kernels gather ONE union neighbour list per cluster of consecutive slots, so every slot pair (2k, 2k+1) should be a
+// pair of close particles: the union of two support spheres (radius 4 lattice spacings) at distance d holds 1.19x (d = 1 spacing)
+// to 1.5x (d = 2.4, what a plain in-cell Morton order gives) the entries of one, and every extra entry is a wasted pair evaluation.
+// One warp per cell re-orders the cell's slot range by a greedy nearest-neighbour matching: seed = first unmatched particle along
+// the Morton curve, mate = its nearest unmatched particle (ties: lower index).  Pairs are aligned to the GLOBAL slot parity (a cell
+// that starts on an odd slot gives its first particle to the pair that straddles the boundary).  Deterministic: a rebuild yields
+// the same order.  Cells with more than PAIR_MAX particles keep the Morton order.
+constexpr int PAIR_MAX = 512;
+__global__ void __launch_bounds__(128) k_pair_cells(const float4* __restrict__ x0m, const int* __restrict__ cell_start, const int* __restrict__ cell_end,
+                                                    int ncells, const uint32_t* __restrict__ perm_in, uint32_t* __restrict__ perm_out) {
+    __shared__ float4 pos[4][PAIR_MAX];
+    __shared__ unsigned short order[4][PAIR_MAX];
+    __shared__ uint32_t used[4][PAIR_MAX / 32];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cell = blockIdx.x * 4 + w;
+    if (cell >= ncells) return;
+    const int b = cell_start[cell], e = cell_end[cell];
+    const int m = e - b;
+    if (m <= 0) return;
+    if (m > PAIR_MAX) {
+        for (int i = lane; i < m; i += 32) perm_out[b + i] = perm_in[b + i];
+        return;
+    }
+    for (int i = lane; i < m; i += 32) pos[w][i] = x0m[b + i];
+    if (lane < PAIR_MAX / 32) used[w][lane] = 0u;
+    __syncwarp();
+    int out = 0;
+    auto take = [&](int i) {                       // all lanes call with the same i
+        if (lane == 0) { used[w][i >> 5] |= 1u << (i & 31); order[w][out] = (unsigned short)i; }
+        out++;
+        __syncwarp();
+    };
+    auto first_unused = [&]() {
+        int f = -1;
+        for (int wd = 0; wd < (m + 31) / 32 && f < 0; wd++) {
+            uint32_t freebits = ~used[w][wd];
+            if (wd == (m - 1) / 32 && (m & 31)) freebits &= (1u << (m & 31)) - 1u;
+            if (freebits) f = wd * 32 + __ffs(freebits) - 1;
+        }
+        return f;
+    };
+    if (b & 1) take(0);                            // odd global slot: half of the pair that straddles the cell boundary
+    while (out < m) {
+        const int seed = first_unused();
+        take(seed);
+        if (out >= m) break;
+        const float4 ps = pos[w][seed];
+        float best = 3.0e38f;
+        int bi = 0x7fffffff;
+        for (int i = lane; i < m; i += 32) {
+            if ((used[w][i >> 5] >> (i & 31)) & 1u) continue;
+            const float4 q = pos[w][i];
+            const float dx = q.x - ps.x, dy = q.y - ps.y, dz = q.z - ps.z;
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            if (d2 < best) { best = d2; bi = i; }                  // ascending i: the lowest index wins a tie inside a lane
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        take(bi);
+    }
+    for (int i = lane; i < m; i += 32) perm_out[b + i] = perm_in[b + order[w][i]];
+}
+// sorted positions and the inverse permutation for the final slot order (mass in .w stays where it is: the order is reproducible)
+__global__ void __launch_bounds__(256) k_apply_order(const uint32_t* __restrict__ perm, const float* __restrict__ x0, int n,
+                                                     int* __restrict__ inv_perm, float4* __restrict__ x0m) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t id = perm[s];
+    inv_perm[id] = s;
+    float* dst = reinterpret_cast<float*>(x0m + s);
+    dst[0] = x0[3 * id]; dst[1] = x0[3 * id + 1]; dst[2] = x0[3 * id + 2];
+}
+
 // Exact membership test.  d2 is formed as ((dx*dx + dy*dy) + dz*dz) with no FMA; the
 // reference predicate sqrt(d2)/h < 2 is monotone in d2, so it equals d2 < d2_limit with
 // d2_limit = the smallest float for which the predicate is false (found on the host with

@@ -219,6 +219,10 @@ class Simulator:
                                              int(pid.numel()), pid.data_ptr(), pp.data_ptr(), ps.data_ptr(),
                                              int(gid.numel()), gid.data_ptr(), self._st()), "mis_halo_connect")
 
+    def halo_set_wait(self, wait: bool):
+        """wait=False: the per-step flag kernel only publishes; the caller orders the ranks by host synchronisation."""
+        native.check(self.L.mis_halo_set_wait(self._h, int(bool(wait))), "mis_halo_set_wait")
+
     def halo_disconnect(self):
         native.check(self.L.mis_halo_disconnect(self._h), "mis_halo_disconnect")
 

@@ -173,7 +173,10 @@ def exchange_volumes_in_process(sims):
 
 
 def connect_in_process(sims):
-    """Fused halo push between ranks that live in ONE process (tests): raw device pointers instead of IPC handles."""
+    """Fused halo push between ranks that live in ONE process on one GPU (tests): raw device pointers instead of IPC handles,
+    and NO in-kernel flag waits -- kernels of different ranks on one GPU are not guaranteed to run at the same time, so the
+    host orders the ranks (step_in_process synchronises between steps).  The push tables, the P2P-store epilogue and the epoch
+    counters are the ones the multi-GPU path uses."""
     ptrs = {s.rank: s.sim.halo_local_ptrs() for s in sims}
     recv_slots = {s.rank: {q: s.sim.slots_of(ids).cpu().numpy() for q, ids in s._recv.items()} for s in sims}
     peer_lists = {s.rank: peers_of(s.plan) for s in sims}
@@ -183,6 +186,7 @@ def connect_in_process(sims):
         flag = [ptrs[q][2] + 4 * peer_lists[q].index(s.rank) for q in peers]
         s.sim.halo_connect([ptrs[q][0] for q in peers], [ptrs[q][1] for q in peers], flag, ids, pidx, slots,
                            np.arange(s.n_owned, s.sim.n, dtype=np.int32))
+        s.sim.halo_set_wait(False)
         s.halo = "p2p"
     for s in sims:
         s.sim.synchronize()
@@ -192,9 +196,15 @@ def step_in_process(sims, n_steps: int = 1):
     """All ranks of a partition driven from ONE process (tests, single-GPU debugging): the same per-step sequence as
     SlabSimulator.step, with the point-to-point exchange replaced by device-to-device copies."""
     if sims and sims[0].halo == "p2p":
-        # the pushes and flag waits are inside each rank's step graph; the ranks' streams run side by side
+        # the pushes are inside each rank's step; one step at a time, host-ordered (see connect_in_process)
         for s in sims:
-            s.sim.step(int(n_steps))
+            s.sim.synchronize()                  # the peers' earlier pushes (priming) have landed
+        for _ in range(int(n_steps)):
+            for s in sims:
+                s.sim.step(1)
+            for s in sims:
+                s.sim.synchronize()
+        for s in sims:
             s.frame += int(n_steps)
         return
 

@@ -160,6 +160,27 @@ def test_trajectory_1000_steps_config1():
     assert np.abs(_np(v) - o.velocity()).max() <= FLOOR_MULT * fv + 2e-5
 
 
+def test_config0_full_size_against_committed_oracle_trajectory():
+    """BASELINE configs[0] at its full size: ~10k-particle sphere, reference defaults, 1000 steps (impact and rebound included),
+    against the oracle trajectory committed under tests/golden/ (made by tests/golden/make_config0_golden.py; ~7 CPU-minutes,
+    which is why it is a fixture).  Tolerance as everywhere: 4 x the oracle's own reorder floor at the same checkpoint."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config0_n10k.npz"))
+    cfg = SceneConfig()
+    x0, _ = scenes.jittered_sphere(10000, seed=0, low_drop=True)
+    assert len(x0) == int(gold["n"]) and float(x0.astype(np.float64).sum()) == float(gold["x0_checksum"])
+    sim = _sim(x0, cfg)
+    sim.startup()
+    done = 0
+    for cp in (100, 500, 1000):
+        sim.step(cp - done); done = cp
+        x, v = sim.position_velocity()
+        dx, dv = np.abs(_np(x) - gold[f"x_{cp}"]).max(), np.abs(_np(v) - gold[f"v_{cp}"]).max()
+        assert dx <= FLOOR_MULT * float(gold[f"floor_x_{cp}"]) + 4e-9, (cp, dx, float(gold[f"floor_x_{cp}"]))
+        assert dv <= FLOOR_MULT * float(gold[f"floor_v_{cp}"]) + 2e-5, (cp, dv, float(gold[f"floor_v_{cp}"]))
+    assert gold["v_1000"][:, 1].mean() > -0.2        # the golden run did hit the ground plane
+
+
 def test_ballistic_is_bit_exact():
     """E = 0 removes the only reordered sums: integration + ground penalty must match bit for bit."""
     x0, _ = scenes.jittered_sphere(1000, seed=3, low_drop=True)

@@ -162,7 +162,10 @@ int mis_export_slots(MisSim* sim, const int* ids_dev, int count, int* slots_dev,
  *   mis_halo_connect     : peer_xv0/xv1[p] = peer p's position buffers mapped here; peer_flag[p] = address of MY entry
  *                          in peer p's flag array (its base + my index in its peer list; MIS_MAX_PEERS entries);
  *                          push_*: for each (owned caller id, peer index, slot on that peer) triple the particle is
- *                          mirrored there (at most two peers per particle); ghost_ids: local particles owned elsewhere.
+ *                          mirrored there (at most two peers per particle); ghost_ids: local particles owned elsewhere;
+ *                          ghost_layer (may be NULL = all 1): 1 = the ghost neighbours an owned particle (its R, S are recomputed
+ *                          locally), 2 = outer layer (only its position is used).  Clusters made of ghosts skip the force gather,
+ *                          clusters made of outer-layer ghosts also the deformation gather (their owner does that work).
  *                          All ranks must have finished their set-up (host barrier) before the first step after connect.
  *   mis_halo_status      : synchronises `stream`; err = 1 if a flag wait timed out (MIS_HALO_TIMEOUT_MS, default 20 s).  */
 #define MIS_MAX_PEERS 4
@@ -172,7 +175,7 @@ int mis_ipc_open(const unsigned char* handle64, void** dev_ptr);
 int mis_ipc_close(void* dev_ptr);
 int mis_halo_connect(MisSim* sim, int n_peers, void* const* peer_xv0, void* const* peer_xv1, void* const* peer_flag,
                      int n_push, const int* push_ids_dev, const int* push_peer_dev, const int* push_slot_dev,
-                     int n_ghost, const int* ghost_ids_dev, void* stream);
+                     int n_ghost, const int* ghost_ids_dev, const int* ghost_layer_dev, void* stream);
 int mis_halo_disconnect(MisSim* sim);
 /* wait = 0: the per-step kernel only publishes this rank's epoch and does NOT wait for the peers'; the caller orders the ranks
  * itself (host synchronisation between steps).  For driving several ranks from one process on ONE GPU (tests), where kernels

@@ -32,6 +32,8 @@ struct MisSim {
     MisParams p{};
     Consts c{};
     int G = 8, C = 2;                 // lanes per cluster, particles per cluster
+    bool merge_lists = false;         // MIS_MERGE_LISTS=1: cluster lists by merging the members' exact lists (2.3x faster rebuild; the appended order costs the
+                                      // force kernel 3-4 % in gather locality, so the 27-cell walk order stays the default)
     bool pair_cells = true;           // MIS_PAIR_CELLS=0: keep the plain in-cell Morton order (A/B measurement)
     // caller-order copies
     float* x0_orig = nullptr;
@@ -199,6 +201,7 @@ extern "C" int mis_create(int n, const float* x0_dev, const MisParams* params, v
     if (Cs != 1 && Cs != 2 && Cs != 4) { delete s; return fail(MIS_E_INVALID, "cluster_size must be 1, 2 or 4"); }
     s->C = Cs;
     { const char* e = getenv("MIS_PAIR_CELLS"); if (e && e[0] == '0') s->pair_cells = false; }
+    { const char* e = getenv("MIS_MERGE_LISTS"); if (e && e[0] == '1') s->merge_lists = true; }
     make_consts(s);
     s->d2_limit = find_d2_limit(s->p.h);
     const size_t N = (size_t)n;
@@ -273,8 +276,11 @@ extern "C" int mis_destroy(MisSim* s) {
 template <int C> static void launch_cluster_walk(MisSim* s, int fill, cudaStream_t st) {
     const int nc = (s->n + C - 1) / C;
     const int3 cdim = make_int3(s->cell_dim[0], s->cell_dim[1], s->cell_dim[2]);
-    k_cluster_walk<C><<<nblk(nc, 128), 128, 0, st>>>(s->x0m, s->cell_lin_sorted, s->cell_start, s->cell_end, cdim, s->n, s->d2_limit, fill,
-                                                     s->cl_start, s->cl, s->cl_count);
+    if (s->merge_lists)
+        k_cluster_merge<C><<<nblk((long long)nc * 32, 128), 128, 0, st>>>(s->x0m, s->nbr_start, s->nbr, s->n, s->d2_limit, fill, s->cl_start, s->cl, s->cl_count);
+    else
+        k_cluster_walk<C><<<nblk(nc, 128), 128, 0, st>>>(s->x0m, s->cell_lin_sorted, s->cell_start, s->cell_end, cdim, s->n, s->d2_limit, fill,
+                                                         s->cl_start, s->cl, s->cl_count);
 }
 static void cluster_walk(MisSim* s, int fill, cudaStream_t st) {
     if (s->C == 1) launch_cluster_walk<1>(s, fill, st); else if (s->C == 2) launch_cluster_walk<2>(s, fill, st); else launch_cluster_walk<4>(s, fill, st);
@@ -892,7 +898,7 @@ extern "C" int mis_ipc_close(void* dev_ptr) {
 
 extern "C" int mis_halo_connect(MisSim* s, int n_peers, void* const* peer_xv0, void* const* peer_xv1, void* const* peer_flag,
                                 int n_push, const int* push_ids_dev, const int* push_peer_dev, const int* push_slot_dev,
-                                int n_ghost, const int* ghost_ids_dev, void* stream) {
+                                int n_ghost, const int* ghost_ids_dev, const int* ghost_layer_dev, void* stream) {
     if (!s || n_peers < 0 || n_peers > MIS_MAX_PEERS || n_push < 0 || n_ghost < 0) return fail(MIS_E_INVALID, "mis_halo_connect: bad argument");
     if (n_peers > 0 && (!peer_xv0 || !peer_xv1 || !peer_flag)) return fail(MIS_E_INVALID, "mis_halo_connect: null peer table");
     if (n_push > 0 && (!push_ids_dev || !push_peer_dev || !push_slot_dev)) return fail(MIS_E_INVALID, "mis_halo_connect: null push list");
@@ -906,7 +912,7 @@ extern "C" int mis_halo_connect(MisSim* s, int n_peers, void* const* peer_xv0, v
     CK(cudaMemsetAsync(s->push, 0xFF, (size_t)s->n * sizeof(int2), st));
     const int m = n_push > n_ghost ? n_push : n_ghost;
     if (m > 0) {
-        k_push_fill<<<nblk(m, 256), 256, 0, st>>>(s->push, s->inv_perm, n_push, push_ids_dev, push_peer_dev, push_slot_dev, n_ghost, ghost_ids_dev);
+        k_push_fill<<<nblk(m, 256), 256, 0, st>>>(s->push, s->inv_perm, n_push, push_ids_dev, push_peer_dev, push_slot_dev, n_ghost, ghost_ids_dev, ghost_layer_dev);
         CK_LAUNCH(); s->launches++;
     }
     for (int p = 0; p < MIS_MAX_PEERS; p++) {

@@ -62,6 +62,20 @@ struct View {
 constexpr int PUSH_GHOST = -2;
 constexpr int PUSH_SLOT_BITS = 28;
 
+// Redundant work of a slab rank: a ghost's force is never used (its owner integrates it), and an outer-layer ghost's R, S neither
+// (only owned particles gather them).  role: 1 = any ghost, 2 = outer-layer ghost.  True if every member of the cluster is >= role.
+template <int C>
+__device__ __forceinline__ bool cluster_is_ghost(const View& s, int cc, int role) {
+    if (!s.push) return false;
+    bool all = true;
+#pragma unroll
+    for (int p = 0; p < C; p++) {
+        const int i = cc * C + p;
+        if (i < s.n) { const int2 pc = s.push[i]; all = all && pc.x == PUSH_GHOST && pc.y >= role; }
+    }
+    return all;
+}
+
 // new position of slot i: local store + stores into the ghost slots of the peers that mirror the particle
 __device__ __forceinline__ void store_next(const View& s, int i, float4 v) {
     if (s.push) {
@@ -120,14 +134,15 @@ __global__ void __launch_bounds__(32) k_halo_sync(HaloSync h) {
 
 // per-slot push table from (caller id, peer, remote slot) triples and the ghost list
 __global__ void __launch_bounds__(256) k_push_fill(int2* __restrict__ push, const int* __restrict__ inv_perm, int n_push, const int* __restrict__ ids,
-                                                   const int* __restrict__ peer, const int* __restrict__ slot, int n_ghost, const int* __restrict__ ghost_ids) {
+                                                   const int* __restrict__ peer, const int* __restrict__ slot, int n_ghost, const int* __restrict__ ghost_ids,
+                                                   const int* __restrict__ ghost_layer) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n_push) {
         const int code = (peer[k] << PUSH_SLOT_BITS) | slot[k];
         int* e = (int*)(push + inv_perm[ids[k]]);
         if (atomicCAS(e, -1, code) != -1) atomicCAS(e + 1, -1, code);      // second mirror of the same particle
     }
-    if (k < n_ghost) push[inv_perm[ghost_ids[k]]].x = PUSH_GHOST;
+    if (k < n_ghost) push[inv_perm[ghost_ids[k]]] = make_int2(PUSH_GHOST, ghost_layer ? ghost_layer[k] : 1);
 }
 __global__ void __launch_bounds__(256) k_slots_of(const int* __restrict__ inv_perm, const int* __restrict__ ids, int count, int* __restrict__ out) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -333,7 +348,8 @@ __global__ void __launch_bounds__(STEP_THREADS, MIS_STEP_MIN_BLOCKS) k_deform_c(
         p0i[p] = s.x0m[i]; pxi[p] = s.xcur[i];
     }
     const unsigned long long b = s.cl_start[cc];
-    const int cnt = (int)(s.cl_start[cc + 1] - b);
+    const bool skip = cluster_is_ghost<C>(s, cc, 2);           // outer-layer ghosts: nobody reads their R, S
+    const int cnt = skip ? 0 : (int)(s.cl_start[cc + 1] - b);
     const uint32_t* __restrict__ lst = s.cl + b;
     const float4* __restrict__ x0m = s.x0m;
     const float4* __restrict__ xcur = s.xcur;
@@ -479,7 +495,7 @@ __global__ void __launch_bounds__(STEP_THREADS, MIS_STEP_MIN_BLOCKS) k_deform_c(
     }
 
     const int i = cc * C + gl;
-    if (gl < C && cid < nc && i < n) {
+    if (gl < C && cid < nc && i < n && !skip) {
         // def_grad = I + N^T
         const float F[9] = {1.f + Nm[0], Nm[3], Nm[6], Nm[1], 1.f + Nm[4], Nm[7], Nm[2], Nm[5], 1.f + Nm[8]};
         const float4 ml = s.matl[i];
@@ -603,7 +619,8 @@ __global__ void __launch_bounds__(STEP_THREADS, MIS_STEP_MIN_BLOCKS) k_force_c(V
         }
     }
     const unsigned long long b = s.cl_start[cc];
-    const int cnt = (int)(s.cl_start[cc + 1] - b);
+    const bool skip = cluster_is_ghost<C>(s, cc, 1);           // ghosts are integrated by their owner
+    const int cnt = skip ? 0 : (int)(s.cl_start[cc + 1] - b);
     const uint32_t* __restrict__ lst = s.cl + b;
 
     float a[C][3];
@@ -671,7 +688,7 @@ __global__ void __launch_bounds__(STEP_THREADS, MIS_STEP_MIN_BLOCKS) k_force_c(V
         if (gl == p) { ax = a[p][0]; ay = a[p][1]; az = a[p][2]; }
 
     const int i = cc * C + gl;
-    if (gl < C && cid < nc && i < n) {
+    if (gl < C && cid < nc && i < n && !skip) {
         const float4 r0 = RS0[i], r1 = RS1[i], r2 = RS2[i], r3 = RS3[i];
         const float4 f0 = Fd0[i], f1 = Fd1[i], f2 = Fd2[i];
         const float4 gs = s.Ks[2 * (size_t)n + i];

@@ -209,13 +209,21 @@ __global__ void __launch_bounds__(128) k_nbr_walk(const float4* __restrict__ x0m
                 if (x < 0 || x >= cdim.x) continue;
                 int c = (z * cdim.y + y) * cdim.x + x;
                 int b = cell_start[c], e = cell_end[c];
-                for (int t = b; t < e; t++) {
-                    if (t == s) continue;
-                    float d2 = dist2_exact(p, x0m[t]);
-                    if (d2 < d2_limit) {
-                        if (fill) out[count] = (uint32_t)t;
-                        count++;
+                // four candidates per trip: the loads do not depend on the tests, so they overlap (the walk is latency-bound)
+                for (int t = b; t < e; t += 4) {
+                    const int t1 = min(t + 1, e - 1), t2 = min(t + 2, e - 1), t3 = min(t + 3, e - 1);
+                    const float4 q0 = x0m[t], q1 = x0m[t1], q2 = x0m[t2], q3 = x0m[t3];
+                    const bool k0 = t != s && dist2_exact(p, q0) < d2_limit;
+                    const bool k1 = t + 1 < e && t1 != s && dist2_exact(p, q1) < d2_limit;
+                    const bool k2 = t + 2 < e && t2 != s && dist2_exact(p, q2) < d2_limit;
+                    const bool k3 = t + 3 < e && t3 != s && dist2_exact(p, q3) < d2_limit;
+                    if (fill) {
+                        if (k0) out[count] = (uint32_t)t;
+                        if (k1) out[count + k0] = (uint32_t)t1;
+                        if (k2) out[count + k0 + k1] = (uint32_t)t2;
+                        if (k3) out[count + k0 + k1 + k2] = (uint32_t)t3;
                     }
+                    count += (uint32_t)k0 + (uint32_t)k1 + (uint32_t)k2 + (uint32_t)k3;
                 }
             }
         }
@@ -224,6 +232,53 @@ __global__ void __launch_bounds__(128) k_nbr_walk(const float4* __restrict__ x0m
         nbr_count[s] = count;
         atomicMax(max_k, (int)count);
     }
+}
+
+// Union neighbour list of every cluster of C consecutive slots from the members' exact lists (one warp per cluster):
+//   union = list(member 0) ++ [ j in list(member 1) : j is not a neighbour of member 0 ] ++ ...
+// "not a neighbour" is one distance test against the earlier members (same exact predicate), so no search is needed and the work is
+// k tests per member instead of 1 728 candidates.  The set equals { j : j is an exact neighbour of at least one member } (a member
+// is listed when it is a neighbour of another member; its own contribution is zero in the step kernels).  fill == 0 counts.
+template <int C>
+__global__ void __launch_bounds__(128) k_cluster_merge(const float4* __restrict__ x0m, const unsigned long long* __restrict__ nbr_start,
+                                                       const uint32_t* __restrict__ nbr, int n, float d2_limit, int fill,
+                                                       const unsigned long long* __restrict__ cl_start, uint32_t* __restrict__ cl,
+                                                       uint32_t* __restrict__ cl_count) {
+    const int nc = (n + C - 1) / C;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (c >= nc) return;
+    const int i0 = c * C;
+    const int m = min(C, n - i0);
+    float4 p[C];
+#pragma unroll
+    for (int q = 0; q < C; q++) p[q] = x0m[min(i0 + q, n - 1)];
+    uint32_t count = 0;
+    uint32_t* out = fill ? cl + cl_start[c] : nullptr;
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int q = 0; q < C; q++) {
+        if (q >= m) break;
+        const unsigned long long b = nbr_start[i0 + q];
+        const int cnt = (int)(nbr_start[i0 + q + 1] - b);
+        for (int k0 = 0; k0 < cnt; k0 += 32) {
+            const int k = k0 + lane;
+            bool keep = k < cnt;
+            uint32_t j = 0;
+            if (keep) {
+                j = nbr[b + k];
+                if (q > 0) {
+                    const float4 pj = x0m[j];
+#pragma unroll
+                    for (int r = 0; r < q; r++)
+                        if ((int)j != i0 + r && dist2_exact(p[r], pj) < d2_limit) keep = false;     // already listed by member r
+                }
+            }
+            const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            if (fill && keep) out[count + __popc(mask & lt)] = j;
+            count += __popc(mask);
+        }
+    }
+    if (!fill && lane == 0) cl_count[c] = count;
 }
 
 // CSR export in caller ids: row i (caller id) <- row inv_perm[i] (sorted), entries mapped by perm

@@ -110,7 +110,7 @@ SYMBOLS = {
     "mis_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "mis_ipc_close": (C.c_int, [_vp]),
     "mis_halo_connect": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
-                                   C.c_int, _ip, _ip, _ip, C.c_int, _ip, _vp]),
+                                   C.c_int, _ip, _ip, _ip, C.c_int, _ip, _ip, _vp]),
     "mis_halo_disconnect": (C.c_int, [_vp]),
     "mis_halo_set_wait": (C.c_int, [_vp, C.c_int]),
     "mis_halo_status": (C.c_int, [_vp, _vp, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),

@@ -207,17 +207,20 @@ class Simulator:
         native.check(self.L.mis_halo_local_ptrs(self._h, C.byref(a), C.byref(b), C.byref(f)), "mis_halo_local_ptrs")
         return int(a.value), int(b.value), int(f.value)
 
-    def halo_connect(self, peer_xv0, peer_xv1, peer_flag, push_ids, push_peer, push_slot, ghost_ids):
+    def halo_connect(self, peer_xv0, peer_xv1, peer_flag, push_ids, push_peer, push_slot, ghost_ids, ghost_layer=None):
         """Switch on the fused halo push (include/mis.h, mis_halo_connect).  Pointer lists are ints (device addresses
         valid in this process); push_* / ghost_ids are int32 arrays."""
         k = len(peer_xv0)
         arr = lambda v: (C.c_void_p * max(1, k))(*[C.c_void_p(int(x)) for x in v])
         dev = lambda a: torch.as_tensor(np.ascontiguousarray(np.asarray(a, np.int32)), device=self.device)
         pid, pp, ps, gid = dev(push_ids), dev(push_peer), dev(push_slot), dev(ghost_ids)
+        gl = dev(ghost_layer) if ghost_layer is not None else None
+        assert gl is None or gl.numel() == gid.numel()
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
         native.check(self.L.mis_halo_connect(self._h, k, arr(peer_xv0), arr(peer_xv1), arr(peer_flag),
                                              int(pid.numel()), pid.data_ptr(), pp.data_ptr(), ps.data_ptr(),
-                                             int(gid.numel()), gid.data_ptr(), self._st()), "mis_halo_connect")
+                                             int(gid.numel()), gid.data_ptr(), gl.data_ptr() if gl is not None else None,
+                                             self._st()), "mis_halo_connect")
 
     def halo_set_wait(self, wait: bool):
         """wait=False: the per-step flag kernel only publishes; the caller orders the ranks by host synchronisation."""

@@ -4,10 +4,10 @@ The reference is single-GPU (no NCCL/MPI call site exists in it).  B
 every neighbour query is centred on the reference position x0 (sim.py:161,178,203,224) -- the partition, the ghost
 sets and the send/receive index lists are STATIC for the whole run:
 
-  * slabs along the longest axis of the x0 bounding box, cut at hash-grid cell boundaries (cell width 2h,
-    sim.py:127) so that owned particle counts are balanced;
-  * a rank keeps two ghost cell layers on each side of its slab: layer 1 (cells adjacent to the slab) holds every
-    neighbour of an owned particle; layer 2 holds every neighbour of a layer-1 particle, so the rank can recompute
+  * slabs along the longest axis of the x0 bounding box, cut at quantiles of that coordinate: owned particle counts
+    are equal to the particle;
+  * a rank keeps two ghost layers of depth 2h (the support radius, sim.py:137-141) on each side of its slab: layer 1
+    holds every neighbour of an owned particle; layer 2 holds every neighbour of a layer-1 particle, so the rank can recompute
     R_j, S_j of its layer-1 ghosts locally (compute_A_pq / compute_nabla_u, sim.py:170-209) and needs ONE exchange
     per step: the new positions (12 B / ghost) written by part_1 (sim.py:247-251);
   * ghosts are pinned locally (free_points = 0, sim.py:285-286) and overwritten by the exchange.
@@ -54,51 +54,48 @@ class RankPlan:
 @dataclass
 class SlabPartition:
     axis: int
-    cuts: np.ndarray                      # world_size + 1 cell coordinates along `axis`: rank r owns cells [cuts[r], cuts[r+1])
+    cuts: np.ndarray                      # world_size + 1 coordinates along `axis`: rank r owns particles with cuts[r] <= x0[axis] < cuts[r+1]
     plans: List[RankPlan]
 
-    @staticmethod
-    def cell_coord(x0: np.ndarray, h: float, axis: int) -> np.ndarray:
-        """int(p * (1 / (2h))) with fp32 arithmetic and truncation, as the hash grid bins x0 (sim.py:127)."""
-        inv = np.float32(1.0) / (np.float32(2.0) * np.float32(h))
-        return np.trunc(np.asarray(x0, np.float32)[:, axis] * inv).astype(np.int64)
-
     @classmethod
-    def build(cls, x0: np.ndarray, h: float, world_size: int, axis: Optional[int] = None, ghost_cells: int = 2) -> "SlabPartition":
+    def build(cls, x0: np.ndarray, h: float, world_size: int, axis: Optional[int] = None, ghost_layers: int = 2) -> "SlabPartition":
+        """Cut planes at quantiles of the x0 coordinate along `axis` (equal owned counts, to the particle); ghost layer L of a
+        rank = foreign particles within L * 2h of its slab along the axis.  Every neighbour (|x0_i - x0_j| < 2h, sim.py:137-141)
+        of an owned particle is owned or layer 1; every neighbour of a layer-1 ghost is local."""
         x0 = np.asarray(x0, np.float32).reshape(-1, 3)
         n = len(x0)
         if axis is None:
             axis = int(np.argmax(x0.max(0) - x0.min(0)))
-        c = cls.cell_coord(x0, h, axis)
-        cmin, cmax = int(c.min()), int(c.max())
-        counts = np.bincount(c - cmin, minlength=cmax - cmin + 1)
-        cum = np.concatenate([[0], np.cumsum(counts)])
-        # cut r at the cell boundary whose cumulative count is closest to r * n / world_size (monotone, non-empty slabs)
-        cuts = [cmin]
-        for r in range(1, world_size):
-            target = r * n / world_size
-            k = int(np.argmin(np.abs(cum - target)))
-            k = max(k, cuts[-1] - cmin + 1)
-            k = min(k, len(counts) - (world_size - r))
-            cuts.append(cmin + k)
-        cuts.append(cmax + 1)
-        cuts = np.asarray(cuts, np.int64)
-        if np.any(np.diff(cuts) < ghost_cells) and world_size > 1:
-            raise ValueError("slabs thinner than the ghost depth: too many ranks for this scene along its longest axis")
+        c = x0[:, axis].astype(np.float64)
         order = np.argsort(c, kind="stable")
-        c_sorted = c[order]
-        def in_cells(lo, hi):              # global ids (ascending) with lo <= cell < hi
-            a, b = np.searchsorted(c_sorted, lo, "left"), np.searchsorted(c_sorted, hi, "left")
+        cs = c[order]
+        reach = 2.0 * float(np.float32(h)) * (1.0 + 1e-4)          # support radius plus a margin far above fp32 rounding of the distance test
+        cuts = [-np.inf]
+        for r in range(1, world_size):
+            k = int(round(r * n / world_size))
+            k = min(max(k, 1), n - 1)
+            cuts.append(0.5 * (cs[k - 1] + cs[k]) if cs[k] > cs[k - 1] else cs[k])
+        cuts.append(np.inf)
+        cuts = np.asarray(cuts, np.float64)
+        inner = np.diff(cuts[1:-1]) if world_size > 2 else np.zeros(0)
+        # an inner slab must contain its neighbours' whole ghost depth (ghosts then come from adjacent ranks only, and a particle
+        # is mirrored on at most two peers); the two end slabs have nobody beyond them
+        if world_size > 1 and (np.any(inner < ghost_layers * reach) or np.any(np.diff(cuts) <= 0)):
+            raise ValueError("slabs thinner than the ghost depth: too many ranks for this scene along its longest axis")
+
+        def in_range(lo, hi):              # global ids (ascending) with lo <= coordinate < hi
+            a, b = np.searchsorted(cs, lo, "left"), np.searchsorted(cs, hi, "left")
             return np.sort(order[a:b])
         plans = []
         for r in range(world_size):
-            lo, hi = int(cuts[r]), int(cuts[r + 1])
-            owned = in_cells(lo, hi)
+            lo, hi = cuts[r], cuts[r + 1]
+            owned = in_range(lo, hi)
             g_ids, g_layer = [], []
-            for layer in range(1, ghost_cells + 1):
-                for a, b in ((lo - layer, lo - layer + 1), (hi + layer - 1, hi + layer)):
-                    ids = in_cells(a, b)
-                    g_ids.append(ids); g_layer.append(np.full(len(ids), layer, np.int32))
+            for layer in range(1, ghost_layers + 1):
+                for a, b in ((lo - layer * reach, lo - (layer - 1) * reach), (hi + (layer - 1) * reach, hi + layer * reach)):
+                    if np.isfinite(a) or np.isfinite(b):
+                        ids = in_range(a, b)
+                        g_ids.append(ids); g_layer.append(np.full(len(ids), layer, np.int32))
             ghosts = np.concatenate(g_ids) if g_ids else np.zeros(0, np.int64)
             layers = np.concatenate(g_layer) if g_layer else np.zeros(0, np.int32)
             o = np.argsort(ghosts, kind="stable")
@@ -185,7 +182,7 @@ def connect_in_process(sims):
         ids, pidx, slots = plan_push(s.plan, peers, {q: recv_slots[q][s.rank] for q in s.plan.send})
         flag = [ptrs[q][2] + 4 * peer_lists[q].index(s.rank) for q in peers]
         s.sim.halo_connect([ptrs[q][0] for q in peers], [ptrs[q][1] for q in peers], flag, ids, pidx, slots,
-                           np.arange(s.n_owned, s.sim.n, dtype=np.int32))
+                           np.arange(s.n_owned, s.sim.n, dtype=np.int32), s.plan.ghost_layer)
         s.sim.halo_set_wait(False)
         s.halo = "p2p"
     for s in sims:
@@ -314,7 +311,7 @@ class SlabSimulator:
             xv0.append(ptr[0]); xv1.append(ptr[1])
             flag.append(ptr[2] + 4 * everyone[q]["peers"].index(self.rank))
         ids, pidx, slots = plan_push(self.plan, peers, {q: everyone[q]["recv_slots"][self.rank] for q in self.plan.send})
-        sim.halo_connect(xv0, xv1, flag, ids, pidx, slots, np.arange(self.n_owned, sim.n, dtype=np.int32))
+        sim.halo_connect(xv0, xv1, flag, ids, pidx, slots, np.arange(self.n_owned, sim.n, dtype=np.int32), self.plan.ghost_layer)
         self.halo = "p2p"
 
     def _exchange(self):

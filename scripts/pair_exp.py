@@ -10,6 +10,16 @@ info = sim.neighbor_info()
 sim.startup(); sim.step(20); sim.synchronize()
 a, b = sim.profile_step(50)
 x = sim.position()
+import torch
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+sim.rebuild_neighbors(); sim.synchronize()
+with torch.cuda.stream(sim.stream):
+    e0.record()
+    for _ in range(5):
+        sim.rebuild_neighbors()
+    e1.record()
+sim.synchronize()
+print("rebuild %.3f ms (merge=%s)" % (e0.elapsed_time(e1) / 5, os.environ.get("MIS_MERGE_LISTS", "1")), end="  ")
 print("pair=%s C=%d n=%d k=%.1f union/k=%.3f deform %.1f us force %.1f us finite=%s" % (
     os.environ.get("MIS_PAIR_CELLS", "1"), info.cluster_size, sim.n, info.total_pairs / sim.n,
     info.union_entries * info.cluster_size / info.total_pairs, 1e3 * a / 50, 1e3 * b / 50, bool(x.isfinite().all())))

@@ -54,6 +54,7 @@ def config0():
 
 
 def config2(n=1_000_000, steps=50):
+    os.environ["MIS_MERGE_LISTS"] = "1"      # rebuild-heavy use: cluster lists merged from the exact lists (faster rebuild, 3 % slower force kernel)
     x0, _ = scenes.jittered_sphere(n, seed=0, low_drop=True)     # resting just above the ground plane (the default centre would bury a 0.2 m sphere)
     n = len(x0)
     t = time.perf_counter()
@@ -89,6 +90,7 @@ def config2(n=1_000_000, steps=50):
                       "particle_steps_per_s_step_only": n * steps / (ms_step * 1e-3), "finite": bool(np.isfinite(x).all()),
                       "max_radial_displacement": float(np.abs(np.linalg.norm(x - x.mean(0), axis=1) - r).max())}), flush=True)
     sim.close()
+    os.environ.pop("MIS_MERGE_LISTS", None)
 
 
 def config3(scenes_per_gpu=8, n=10000, steps=512):

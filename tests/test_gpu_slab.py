@@ -92,11 +92,14 @@ def test_ghost_volumes_and_strained_forces_match_single_domain():
         before = max(before, np.abs(f - f1[s.plan.owned]).max())
     exchange_volumes_in_process(sims)
     after = 0.0
+    owner_vol = np.zeros(len(x0), np.float32)
+    for s in sims:
+        owner_vol[s.plan.owned] = s.sim.volumes().cpu().numpy()[: s.n_owned]
     for s in sims:
         v = s.sim.volumes().cpu().numpy()
         layer1 = s.n_owned + np.nonzero(s.plan.ghost_layer == 1)[0]
-        assert np.array_equal(v[s.n_owned:], vol1[s.plan.ghosts])            # ghosts carry their owner's value, bit for bit
-        assert np.allclose(v[: s.n_owned], vol1[s.plan.owned], rtol=2e-6)     # owned: same sum, local summation order
+        assert np.array_equal(v[s.n_owned:], owner_vol[s.plan.ghosts])       # ghosts carry their owner's value, bit for bit
+        assert np.allclose(v, vol1[s.plan.local_ids], rtol=2e-6)              # = the single-domain sum up to the local summation order
         assert len(layer1) > 0
         f = s.sim.eval_forces(xs[s.plan.local_ids]).cpu().numpy()[: s.n_owned]
         after = max(after, np.abs(f - f1[s.plan.owned]).max())

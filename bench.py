@@ -166,6 +166,17 @@ def workload_config(args, n_total, mean_k, world, mode, extra=None):
          "l2": "flushed between timed steps (256 MiB device write outside the event pairs); steady_state = un-flushed chained steps"}
     if extra:
         c.update(extra)
+    if world > 1 and mode == "slab":
+        # the N = 1 bench line is configs[1] (100k particles + obstacle), not this workload: point at the measured single-GPU
+        # throughput of ONE GPU's share of this scene (same per-GPU particle count, no partition) as the weak-scaling denominator
+        try:
+            for l in open(os.path.join(ROOT, "profiles", "r01_scaling.jsonl")):
+                d = json.loads(l)
+                if d.get("run") == "n1_1250k" and abs(d["config"]["n_particles"] - args.n) < 0.01 * args.n:
+                    c["single_gpu_same_share"] = {"value": d["value"], "unit": UNIT, "n_particles": d["config"]["n_particles"],
+                                                  "source": "profiles/r01_scaling.jsonl run n1_1250k (bench.py --n 1250000 --no-obstacle)"}
+        except Exception:
+            pass
     return c
 
 

@@ -259,14 +259,19 @@ class SlabSimulator:
         self._mapped = []
         if world_size > 1 and not in_process:
             self._exchange_volumes()
+            requested = halo
             if halo == "auto":
                 import os
                 local = int(os.environ.get("LOCAL_WORLD_SIZE", world_size))
                 halo = "p2p" if local == world_size else "nccl"
-            if halo == "p2p":
-                self._connect_p2p()
-            elif halo != "nccl":
+            if halo not in ("p2p", "nccl"):
                 raise ValueError("halo must be 'auto', 'p2p' or 'nccl'")
+            if halo == "p2p":
+                err = self._connect_p2p()
+                if err is not None:                  # agreed by all ranks: nobody is connected
+                    if requested == "p2p":
+                        raise RuntimeError("fused halo push unavailable: " + err)
+                    self.halo = "nccl"               # 'auto' falls back to the NCCL exchange
 
     # halo plumbing -----------------------------------------------------------------------------------------
     def _exchange_volumes(self):
@@ -291,28 +296,51 @@ class SlabSimulator:
 
     def _connect_p2p(self):
         """Exchange CUDA IPC handles of the position buffers / flag arrays and the ghosts' slots, map the peers' memory,
-        and hand the push table to the library (mis_halo_connect)."""
+        and hand the push table to the library (mis_halo_connect).  Collective: every rank takes part in both exchanges even
+        if a local step failed, and all ranks agree on the outcome.  Returns None on success, else the first error message
+        (no rank is connected then)."""
         import ctypes as C
+        import torch
         from . import native
         sim = self.sim
         peers = peers_of(self.plan)
-        mine = {"handles": sim.halo_ipc_handles(), "peers": peers,
-                "recv_slots": {q: sim.slots_of(ids).cpu().numpy() for q, ids in self._recv.items()}}
+        mine = {"peers": peers, "error": None}
+        try:
+            mine["handles"] = sim.halo_ipc_handles()
+            mine["recv_slots"] = {q: sim.slots_of(ids).cpu().numpy() for q, ids in self._recv.items()}
+        except Exception as e:                       # e.g. CUDA IPC not permitted in this container
+            mine["error"] = f"rank {self.rank}: {e}"
         everyone = [None] * self.world
         self.dist.all_gather_object(everyone, mine, group=self.group)
-        xv0, xv1, flag = [], [], []
-        for q in peers:
-            h = everyone[q]["handles"]
-            ptr = []
-            for k in range(3):
-                p = C.c_void_p()
-                native.check(sim.L.mis_ipc_open(h[64 * k: 64 * k + 64], C.byref(p)), "mis_ipc_open")
-                ptr.append(int(p.value)); self._mapped.append(int(p.value))
-            xv0.append(ptr[0]); xv1.append(ptr[1])
-            flag.append(ptr[2] + 4 * everyone[q]["peers"].index(self.rank))
-        ids, pidx, slots = plan_push(self.plan, peers, {q: everyone[q]["recv_slots"][self.rank] for q in self.plan.send})
-        sim.halo_connect(xv0, xv1, flag, ids, pidx, slots, np.arange(self.n_owned, sim.n, dtype=np.int32), self.plan.ghost_layer)
-        self.halo = "p2p"
+        error = next((m["error"] for m in everyone if m["error"]), None)
+        if error is None:
+            try:
+                xv0, xv1, flag = [], [], []
+                for q in peers:
+                    h = everyone[q]["handles"]
+                    ptr = []
+                    for k in range(3):
+                        p = C.c_void_p()
+                        native.check(sim.L.mis_ipc_open(h[64 * k: 64 * k + 64], C.byref(p)), "mis_ipc_open")
+                        ptr.append(int(p.value)); self._mapped.append(int(p.value))
+                    xv0.append(ptr[0]); xv1.append(ptr[1])
+                    flag.append(ptr[2] + 4 * everyone[q]["peers"].index(self.rank))
+                ids, pidx, slots = plan_push(self.plan, peers, {q: everyone[q]["recv_slots"][self.rank] for q in self.plan.send})
+                sim.halo_connect(xv0, xv1, flag, ids, pidx, slots, np.arange(self.n_owned, sim.n, dtype=np.int32), self.plan.ghost_layer)
+            except Exception as e:                   # e.g. no peer access between two of the GPUs
+                error = f"rank {self.rank}: {e}"
+        ok = torch.tensor([0 if error else 1], dtype=torch.int32, device=self.device)
+        self.dist.all_reduce(ok, op=self.dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            self.halo = "p2p"
+            return None
+        errors = [None] * self.world
+        self.dist.all_gather_object(errors, error, group=self.group)
+        sim.halo_disconnect()
+        for p in self._mapped:
+            sim.L.mis_ipc_close(p)
+        self._mapped = []
+        return next((e for e in errors if e), "unknown error")
 
     def _exchange(self):
         if self.world == 1 or self.in_process or self.halo == "p2p":

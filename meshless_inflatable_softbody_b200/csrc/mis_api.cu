@@ -300,8 +300,8 @@ static int build_cluster_lists(MisSim* s, cudaStream_t st) {
     if (s->cl_total > s->cl_cap || !s->cl) {
         if (s->cl) cudaFree(s->cl);
         s->cl = nullptr;
-        CK(dalloc(&s->cl, (size_t)s->cl_total + 64));
-        CK(cudaMemsetAsync(s->cl, 0, ((size_t)s->cl_total + 64) * sizeof(uint32_t), st));
+        CK(dalloc(&s->cl, (size_t)s->cl_total + LIST_PAD));
+        CK(cudaMemsetAsync(s->cl, 0, ((size_t)s->cl_total + LIST_PAD) * sizeof(uint32_t), st));
         s->cl_cap = s->cl_total;
     }
     cluster_walk(s, 1, st);

@@ -176,6 +176,7 @@ constexpr int STEP_THREADS = MIS_STEP_THREADS;
 #define MIS_IDX_AHEAD 2
 #endif
 constexpr int IDX_AHEAD = MIS_IDX_AHEAD;
+constexpr int LIST_PAD = 1024;                  // zero entries behind the last union list: >= (IDX_AHEAD + 3) * G for every G
 // union-list entries are read once per launch.  Keeping them out of L1 (MIS_IDX_NOALLOC) was measured SLOWER on B200
 // (deform 155 vs 145 us at n = 1e5): the default is a plain cached load.
 __device__ __forceinline__ uint32_t ld_idx(const uint32_t* p) {
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(STEP_THREADS, MIS_STEP_MIN_BLOCKS) k_deform_c(
 
     // Software pipeline: indices are fetched IDX_AHEAD entries ahead (2, 4 and 8 measured the same on B200: the index stream is not
     // what the loop waits for); the gathered record of entry k + G is in flight while entry k is consumed.  Unrolled by two (dA: even entries of this lane,
-    // dB: odd ones) so the in-flight record is never moved between registers.  The lists are padded with 64 zero entries.
+    // dB: odd ones) so the in-flight record is never moved between registers.  Index loads are guarded here (measured: 134 vs 140 us unguarded; the force kernel is the other way round, 110.5 vs 112.6 us, and reads past the end of a list: the next cluster's list or the LIST_PAD zero entries behind the last one).
     auto eval = [&](const DeformJ& d) {
 #pragma unroll
         for (int p = 0; p < C; p++) {
@@ -661,16 +662,16 @@ __global__ void __launch_bounds__(STEP_THREADS, MIS_STEP_MIN_BLOCKS) k_force_c(V
         int k = gl;
         uint32_t q[IDX_AHEAD];
 #pragma unroll
-        for (int t = 0; t < IDX_AHEAD; t++) q[t] = (k + (t + 1) * G < cnt) ? ld_idx(lst + k + (t + 1) * G) : 0u;
+        for (int t = 0; t < IDX_AHEAD; t++) q[t] = ld_idx(lst + k + (t + 1) * G);
         ForceJ dA, dB;
-        load(dA, (k < cnt) ? ld_idx(lst + k) : 0u);
+        load(dA, ld_idx(lst + k));
         while (k < cnt) {
             load(dB, q[0]);
-            const uint32_t n0 = (k + (IDX_AHEAD + 1) * G < cnt) ? ld_idx(lst + k + (IDX_AHEAD + 1) * G) : 0u;
+            const uint32_t n0 = ld_idx(lst + k + (IDX_AHEAD + 1) * G);
             eval(dA);
             if (k + G >= cnt) break;
             load(dA, q[1]);
-            const uint32_t n1 = (k + (IDX_AHEAD + 2) * G < cnt) ? ld_idx(lst + k + (IDX_AHEAD + 2) * G) : 0u;
+            const uint32_t n1 = ld_idx(lst + k + (IDX_AHEAD + 2) * G);
             eval(dB);
 #pragma unroll
             for (int t = 0; t + 2 < IDX_AHEAD; t++) q[t] = q[t + 2];

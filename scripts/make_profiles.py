@@ -2,7 +2,7 @@
 
     python scripts/make_profiles.py r01
 
-Inputs (produced by scripts/job4.sh and scripts/job_multi.sh under gpurun): bench_j.json, launches_j.csv, raw_j.csv (= `ncu -i
+Inputs (produced by scripts/gpu_job_profile.sh and scripts/gpu_job_multi.sh under gpurun): bench_j.json, launches_j.csv, raw_j.csv (= `ncu -i
 prof_r01_j.ncu-rep --page raw --csv`), configs_j.jsonl, bench_n*.json."""
 import csv
 import json
@@ -59,6 +59,24 @@ with open(os.path.join(P, f"{tag}_ncu_full_summary.csv"), "w", newline="") as f:
         traffic.setdefault(key, {"bytes_per_launch_n100k": rd + wr, "read": rd, "write": wr,
                                  "source": f"ncu --set full, {tag}_ncu_full_summary.csv (first profiled launch of the kernel)"})
 json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
+# HBM-bound kernels (cell binning / radix sort, stand-alone integrate, export) at n = 1e6: raw_build.csv from scripts/gpu_job_build_profile.sh
+braw = os.path.join(G, "raw_build.csv")
+if os.path.exists(braw):
+    rows = list(csv.reader(open(braw)))
+    hdr, units = rows[0], rows[1]
+    col = lambda r, m: r[hdr.index(m)]
+    scale = {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}
+    tscale = {"us": 1e-6, "ms": 1e-3, "ns": 1e-9, "s": 1.0}
+    with open(os.path.join(P, f"{tag}_ncu_build_n1m.csv"), "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["kernel", "time_us", "dram_read_MB", "dram_write_MB", "achieved_GBps", "dram_pct_of_peak", "l2_pct_of_peak", "grid", "block"])
+        for r in rows[2:]:
+            t = float(col(r, "gpu__time_duration.sum")) * tscale[units[hdr.index("gpu__time_duration.sum")]]
+            rd = float(col(r, "dram__bytes_read.sum")) * scale[units[hdr.index("dram__bytes_read.sum")]]
+            wr = float(col(r, "dram__bytes_write.sum")) * scale[units[hdr.index("dram__bytes_write.sum")]]
+            w.writerow([col(r, "Kernel Name").split("(")[0].replace("void ", ""), round(t * 1e6, 2), round(rd / 1e6, 2), round(wr / 1e6, 2),
+                        round((rd + wr) / t / 1e9, 1), col(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                        col(r, "lts__throughput.avg.pct_of_peak_sustained_elapsed"), col(r, "launch__grid_size"), col(r, "launch__block_size")])
 shutil.copy(os.path.join(G, "configs_j.jsonl"), os.path.join(P, f"{tag}_configs.jsonl"))
 with open(os.path.join(P, f"{tag}_scaling.jsonl"), "w") as f:
     for name in sorted(os.listdir(G)):

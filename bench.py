@@ -437,7 +437,7 @@ def run_ours(args, cfg, rank, world, local_rank):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": kern[dom]["gbs"] / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": kern[dom]["gbs"] / hbm_peak, "frac_of_spec_8000": kern[dom]["gbs"] / 8000.0, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": nloc * kern[dom]["bytes_per_particle"], "launch_ms": kern[dom]["ms"],
                 "note": "at ~240 neighbours/particle the gather kernels are FP32-pipe / L1 bound, not HBM bound (SURVEY 8d): "
                         "fp32_fraction (algorithmic flops / measured FFMA peak) is the binding figure",

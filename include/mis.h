@@ -191,6 +191,10 @@ int mis_get_fields(MisSim* sim, float* A_dev, float* R_dev, float* F_dev, float*
 /* Evaluate the elastic force at an arbitrary configuration x (n*3) without touching the
  * state: compute_A_pq -> compute_nabla_u -> compute_elastic_forces once.              */
 int mis_eval_forces(MisSim* sim, const float* x_dev, float* fel_dev, void* stream);
+/* compute_loss, sim.py:269-273, forward value only: loss_dev[0] (fp64, device) += sum_i |x_i - xt_i|^2 + time_step |v_i - vt_i|^2
+ * at the current frame; targets are n*3 fp32 in caller order (the position_{i}.npy / velocity_{i}.npy of sim.py:118-119).
+ * Deterministic (fixed summation order).  The reverse pass (wp.Tape, sim.py:346-372) is out of scope.                       */
+int mis_accumulate_loss(MisSim* sim, const float* target_x_dev, const float* target_v_dev, double* loss_dev, void* stream);
 /* number of kernels this sim has launched so far (bench.py's gpu_launches)           */
 long long mis_launch_count(MisSim* sim);
 /* Measurement aid: n_steps steps with a CUDA event pair around every kernel launch on

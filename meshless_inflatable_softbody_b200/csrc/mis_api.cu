@@ -72,6 +72,7 @@ struct MisSim {
     float4 *fext = nullptr, *freem = nullptr, *matl = nullptr, *RS = nullptr, *Fd = nullptr, *Ks = nullptr;
     float* Apq = nullptr;
     float4* scratch4 = nullptr;       // eval / host staging
+    double* loss_partial = nullptr;   // block partial sums of mis_accumulate_loss
     float* stage = nullptr;           // n*6 device staging for host-buffer variants
     int cur = 0;
     bool built = false, mass_set = false, material_set = false, started = false, dirty = true;
@@ -263,7 +264,7 @@ extern "C" int mis_destroy(MisSim* s) {
         cudaStreamDestroy(s->copy_stream);
         if (s->up_stream) { cudaStreamSynchronize(s->up_stream); cudaStreamDestroy(s->up_stream); }
     }
-    void* ptrs[] = {s->push, s->halo_mem, s->con_idx, s->con_idx2, s->con_count, s->con_pts, s->con_pts2, s->con_s0, s->fcon, s->x0_orig, s->coords, s->cell_index, s->keys, s->subkey, s->Ks, s->perm, s->inv_perm, s->rs.keys_alt, s->rs.vals_alt,
+    void* ptrs[] = {s->loss_partial, s->push, s->halo_mem, s->con_idx, s->con_idx2, s->con_count, s->con_pts, s->con_pts2, s->con_s0, s->fcon, s->x0_orig, s->coords, s->cell_index, s->keys, s->subkey, s->Ks, s->perm, s->inv_perm, s->rs.keys_alt, s->rs.vals_alt,
                     s->rs.hist, s->rs.hist_scanned, s->rs.tile_tmp, s->bounds_dev, s->max_k_dev, s->cell_start, s->cell_end,
                     s->cell_lin_sorted, s->nbr_count, s->nbr_start, s->scan_tmp, s->nbr, s->cl_count, s->cl_start, s->cl, s->x0m, s->xv[0], s->xv[1], s->vel,
                     s->f1, s->fel, s->fext, s->freem, s->matl, s->RS, s->Fd, s->Apq, s->scratch4, s->stage};
@@ -955,6 +956,19 @@ extern "C" int mis_halo_status(MisSim* s, void* stream, int* err, long long* exc
     CK(cudaMemcpy(host, s->halo_mem + MIS_MAX_PEERS, sizeof host, cudaMemcpyDeviceToHost));
     if (err) *err = (int)host[1];
     if (exchanges) *exchanges = (long long)host[0];                  // counted on the device: graph replays included
+    return MIS_OK;
+}
+
+extern "C" int mis_accumulate_loss(MisSim* s, const float* target_x_dev, const float* target_v_dev, double* loss_dev, void* stream) {
+    if (!s || !target_x_dev || !target_v_dev || !loss_dev) return fail(MIS_E_INVALID, "null argument");
+    if (!s->started) return fail(MIS_E_STATE, "mis_accumulate_loss before mis_startup / mis_set_state");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = 296;                                        // 2 per SM
+    if (!s->loss_partial) CK(dalloc(&s->loss_partial, (size_t)blocks));
+    double* partial = s->loss_partial;
+    k_loss_partial<<<blocks, 256, 0, st>>>(s->xv[s->cur], s->vel, s->inv_perm, target_x_dev, target_v_dev, s->n, s->p.dt, partial);
+    k_loss_final<<<1, 1, 0, st>>>(partial, blocks, loss_dev);
+    CK_LAUNCH(); s->launches += 2;
     return MIS_OK;
 }
 

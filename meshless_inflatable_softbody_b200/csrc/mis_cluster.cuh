@@ -776,6 +776,38 @@ __global__ void __launch_bounds__(256) k_subset_scatter(float4* __restrict__ dst
     float4* d = dst + inv_perm[ids[k]];
     d->x = in[3 * (size_t)k]; d->y = in[3 * (size_t)k + 1]; d->z = in[3 * (size_t)k + 2];   // .w (volume) untouched
 }
+// compute_loss, sim.py:269-273: l += |x_i - xt_i|^2 + time_step |v_i - vt_i|^2 per particle (fp32 terms as in the reference; the
+// reference sums them with fp32 atomics in arbitrary order -- here: fp64 block partials, then a fixed-order final sum: deterministic).
+__global__ void __launch_bounds__(256) k_loss_partial(const float4* __restrict__ x, const float4* __restrict__ v, const int* __restrict__ inv_perm,
+                                                      const float* __restrict__ tx, const float* __restrict__ tv, int n, float dt,
+                                                      double* __restrict__ partial) {
+    __shared__ double sm[8];
+    double acc = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int sl = inv_perm[i];
+        const float4 px = x[sl], pv = v[sl];
+        const float dx = px.x - tx[3 * (size_t)i], dy = px.y - tx[3 * (size_t)i + 1], dz = px.z - tx[3 * (size_t)i + 2];
+        const float ex = pv.x - tv[3 * (size_t)i], ey = pv.y - tv[3 * (size_t)i + 1], ez = pv.z - tv[3 * (size_t)i + 2];
+        const float a = dx * dx + dy * dy + dz * dz;                   // wp.length_sq
+        const float b = (ex * ex + ey * ey + ez * ez) * dt;
+        acc += (double)a + (double)b;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += sm[w];
+        partial[blockIdx.x] = t;
+    }
+}
+__global__ void k_loss_final(const double* __restrict__ partial, int nblocks, double* __restrict__ loss) {
+    double t = 0.0;
+    for (int b = 0; b < nblocks; b++) t += partial[b];
+    loss[0] += t;
+}
+
 // export fields: which = 0 R, 1 S (full symmetric 3x3), 2 F, 3 A, 4 rho, 5 vol
 __global__ void __launch_bounds__(256) k_export_field(View s, const int* __restrict__ inv_perm, int which, float* __restrict__ dst) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

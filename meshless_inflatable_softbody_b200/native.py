@@ -99,6 +99,7 @@ SYMBOLS = {
     "mis_wait_state_host": (C.c_int, [_vp, C.c_int]),
     "mis_get_fields": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp]),
     "mis_eval_forces": (C.c_int, [_vp, _fp, _fp, _vp]),
+    "mis_accumulate_loss": (C.c_int, [_vp, _fp, _fp, _vp, _vp]),
     "mis_launch_count": (C.c_longlong, [_vp]),
     "mis_profile_step": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mis_gather_next_positions": (C.c_int, [_vp, _ip, C.c_int, _fp, _vp]),

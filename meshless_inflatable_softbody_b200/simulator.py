@@ -337,6 +337,34 @@ class Simulator:
             np.save(os.path.join(folder, f"position_{i}.npy"), x.cpu().numpy())
             np.save(os.path.join(folder, f"velocity_{i}.npy"), v.cpu().numpy())
 
+    def accumulate_loss(self, target_x, target_v, loss: torch.Tensor):
+        """compute_loss (sim.py:269-273) at the current frame: loss[0] (fp64 device tensor) += sum |x - xt|^2 + dt |v - vt|^2."""
+        tx, tv = self._dev(target_x, (self.n, 3)), self._dev(target_v, (self.n, 3))
+        assert loss.dtype == torch.float64 and loss.is_cuda
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        native.check(self.L.mis_accumulate_loss(self._h, tx.data_ptr(), tv.data_ptr(), loss.data_ptr(), self._st()), "mis_accumulate_loss")
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)     # keeps tx / tv alive until the kernel has read them
+
+    def rollout_loss(self, targets, frames: Optional[int] = None) -> float:
+        """Forward value of the reference's objective (diff_sim without the tape, sim.py:341-362): startup, `frames` steps, and
+        compute_loss against target i at frame (frames // len(targets)) * (i + 1).  targets: a folder holding
+        position_{i}.npy / velocity_{i}.npy (i = 1..), as export_targets writes them, or a list of (x, v) arrays."""
+        if isinstance(targets, (str, os.PathLike)):
+            k, pairs = 1, []
+            while os.path.exists(os.path.join(targets, f"position_{k}.npy")):
+                pairs.append((np.load(os.path.join(targets, f"position_{k}.npy")), np.load(os.path.join(targets, f"velocity_{k}.npy"))))
+                k += 1
+            targets = pairs
+        frames = frames or self.cfg.frames
+        every = frames // len(targets)
+        loss = torch.zeros(1, dtype=torch.float64, device=self.device)
+        self.startup()
+        for tx, tv in targets:
+            self.step(every)
+            self.accumulate_loss(tx, tv, loss)
+        self.stream.synchronize()
+        return float(loss.item())
+
     # ------------------------------------------------------------------ neighbour structure (bit-exact checks)
     def neighbor_info(self) -> native.MisNeighborInfo:
         info = native.MisNeighborInfo()

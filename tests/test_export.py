@@ -49,3 +49,33 @@ def test_recorded_frames_equal_direct_readback():
         assert np.array_equal(xs[k], x.cpu().numpy()[:out_num])          # same kernels, same order: bit-identical
         assert np.array_equal(vs[k], v.cpu().numpy()[:out_num])
     assert np.array_equal(xs[0], x0[:out_num])                          # frame 0 = the reference configuration (sim.py:261-266)
+
+
+@pytest.mark.gpu
+def test_rollout_loss_matches_the_reference_formula(tmp_path):
+    """compute_loss (sim.py:269-273) over the target frames, forward value: targets written by export_targets of one scene, loss of a
+    second scene with a different design field against them, checked against the same sum formed in fp64 from the exported states;
+    and a scene against its own targets has zero loss."""
+    import torch
+    from meshless_inflatable_softbody_b200 import Simulator, SceneConfig, scenes
+    x0, out_num = scenes.jittered_sphere(1200, seed=1, low_drop=True)
+    cfg = SceneConfig()
+    a = Simulator(x0, cfg)
+    a.startup()
+    a.export_targets(str(tmp_path), every=20, count=3)                 # frames 20, 40, 60
+    same = Simulator(x0, cfg)
+    assert same.rollout_loss(str(tmp_path), frames=60) == 0.0
+    b = Simulator(x0, cfg)
+    xd = np.full(len(x0), -1.0, np.float32); xd[:out_num] = 0.5        # softer shell
+    b.set_design(xd)
+    got = b.rollout_loss(str(tmp_path), frames=60)
+    c = Simulator(x0, cfg)
+    c.set_design(xd); c.startup()
+    want = 0.0
+    for i in (1, 2, 3):
+        c.step(20)
+        x, v = (t.cpu().numpy().astype(np.float64) for t in c.position_velocity())
+        tx, tv = np.load(tmp_path / f"position_{i}.npy").astype(np.float64), np.load(tmp_path / f"velocity_{i}.npy").astype(np.float64)
+        want += ((x - tx) ** 2).sum() + float(np.float32(cfg.time_step)) * ((v - tv) ** 2).sum()
+    assert got > 0.0 and abs(got - want) <= 1e-5 * want
+    assert b.rollout_loss(str(tmp_path), frames=60) == got             # fixed summation order: reproducible to the bit

@@ -1043,7 +1043,6 @@ extern "C" int mis_sdf_create(int n_layers, const int* dims, const float* const*
         }
     }
     SALLOC(s->bslab, hidden * (size_t)H);
-    { float* sy = nullptr; SALLOC(sy, 16); s->chain_sync = (unsigned*)sy; cudaMemsetAsync(sy, 0, 16 * sizeof(float), st); }
     { const char* e = getenv("MIS_SDF_CHAIN"); if (e && e[0] == '0') s->chain_mode = 0; }
     for (int l = 1; l < n_layers - 1; l++) {
         float *hi = s->Wslab + (size_t)(l - 1) * 2 * H * H, *lo = hi + (size_t)H * H, *b = s->bslab + (size_t)(l - 1) * H;

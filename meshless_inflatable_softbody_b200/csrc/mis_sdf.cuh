@@ -496,28 +496,41 @@ k_sdf_gemm_sk(const float* __restrict__ Xhi, const float* __restrict__ Xlo, cons
 //     FIXED rank order (deterministic, and the same order as k_sdf_gemm_sk: bit-identical results); rank r finishes 16 columns.
 //     H / 128 clusters = 64 CTAs at H = 1024: a cooperative launch accepts at most 15 co-resident 8-CTA clusters on a B200 (measured:
 //     cudaOccupancyMaxActiveClusters), which rules out the 16 clusters of 64-column tiles;
-//   * the grid meets at a device-wide barrier between layers: epilogue threads fence + count in, the TMA producer of every CTA waits
-//     for the count before it loads the new activations.  Cooperative launch => all CTAs are co-resident, the wait cannot deadlock;
+//   * dependencies between layers are tracked per (row-block, column tile): the K slice a CTA reads is produced by the CTAs of the
+//     cluster(s) owning those columns, which count in (fence + release add) when their part of a row-block is stored; the TMA producer
+//     waits only for the tiles it is about to load.  Row-blocks therefore flow through the layers as a wavefront instead of meeting
+//     at a device-wide barrier.  Cooperative launch => all CTAs are co-resident, the waits cannot deadlock.  The two ping-pong
+//     activation buffers stay safe: a column tile of a row-block is overwritten (layer l + 1) only after the whole writing cluster
+//     holds the layer-l outputs of ALL clusters for that row-block, i.e. after every reader of the old contents has finished;
 //   * the W tiles of the next layer's first k-blocks do not depend on the activations: they are issued into the ring BEFORE the barrier
 //     wait (same stage barrier; the A halves complete the transaction count afterwards);
-//   * the partial tile has its own 64 KB of shared memory, so the producer runs ahead of the epilogue; only the MMA issuer waits for the
-//     previous tile's epilogue (the accumulator is single-buffered).
+//   * the partial tile has its own 64 KB of shared memory and the accumulator is double-buffered in TMEM (2 x 128 columns), so loads and
+//     MMAs of the next tile run under the drain / reduce / store of the current one.
 constexpr int CH_BN = 128;
 constexpr int CH_STAGES = 2;
 constexpr int CH_STAGE_BYTES = 4 * SDF_TILE_BYTES;                         // A_hi, A_lo, W_hi, W_lo of one k-block: 64 KB
 constexpr int CH_STAGING_BYTES = SDF_BM * CH_BN * 4;                       // 64 KB fp32 partial tile
-constexpr int CH_TMEM_COLS = 128;
+constexpr int CH_TMEM_COLS = 256;                                         // two 128-column accumulators: the MMAs of tile t + 1 run while tile t is drained
 constexpr int CH_SMEM_BYTES = CH_STAGES * CH_STAGE_BYTES + CH_STAGING_BYTES + 256 + 1024;
+constexpr int CH_THREADS = SDF_THREADS + 32;                             // + one warp that publishes finished tiles (fence + release) off the epilogue's path
+
+#ifdef MIS_CHAIN_TIMING
+// phase timestamps of CTA MIS_CHAIN_TIMING, 16 slots per tile (scripts/ubench/chain_timing.cu)
+__device__ unsigned long long ch_dbg[16 * 64];
+#define CH_T(tile, k) do { if (blockIdx.x == MIS_CHAIN_TIMING && (tile) < 64) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); ch_dbg[(tile) * 16 + (k)] = t_; } } while (0)
+#else
+#define CH_T(tile, k) do { } while (0)
+#endif
 
 struct SkChain {
     const float* W;          // hidden-layer weights, contiguous: layer l = [hi plane H*H | lo plane H*H] at W + l * 2 H H (UMMA tiles)
     const float* bias;       // [n_layers][H]
     float* act[2][2];        // ping-pong activations [buffer][hi / lo]; layer l reads buffer l & 1, writes (l + 1) & 1
     int n_layers;
-    unsigned* sync;          // [0] device-wide barrier count, [1] exit count (the last CTA out zeroes both for the next launch)
+    unsigned* sync;          // [0] exit count, [1] unused, [2 + mb * NT + tile] arrivals of (row-block mb, column tile); the last CTA out zeroes what was used
 };
 
-__global__ void __cluster_dims__(SK_SPLIT, 1, 1) __launch_bounds__(SDF_THREADS, 1)
+__global__ void __cluster_dims__(SK_SPLIT, 1, 1) __launch_bounds__(CH_THREADS, 1)
 k_sdf_chain_sk(SkChain c, int H, int m_rows, const int* __restrict__ m_count) {
     extern __shared__ uint8_t smem_raw[];
     const int nb = blockIdx.x / SK_SPLIT;                      // cluster id = column tile (gridDim.x = (H / 128) * 8 exactly)
@@ -529,17 +542,20 @@ k_sdf_chain_sk(SkChain c, int H, int m_rows, const int* __restrict__ m_count) {
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t stg_sm = base + CH_STAGES * CH_STAGE_BYTES; // partial tile
     const uint32_t bars = stg_sm + CH_STAGING_BYTES;
-    // full[s] +8 s | empty[s] +16 + 8 s | tfull +32 | stg_done +40 | ready +48 | freeb +56 | tmem pointer +64
-    const uint32_t BAR_F = bars, BAR_E = bars + 16, BAR_TF = bars + 32, BAR_SD = bars + 40, BAR_RDY = bars + 48, BAR_FREE = bars + 56,
-                   TMEM_SLOT = bars + 64;
+    // full[s] +8 s | empty[s] +16 + 8 s | tfull[b] +32 + 8 b | drained[b] +48 + 8 b | ready +64 | consumed +72 | stored[b] +80 + 8 b |
+    // published[b] +96 + 8 b | tmem pointer +112
+    const uint32_t BAR_F = bars, BAR_E = bars + 16, BAR_TF = bars + 32, BAR_SD = bars + 48, BAR_RDY = bars + 64, BAR_CONS = bars + 72,
+                   BAR_ST = bars + 80, BAR_STA = bars + 96, TMEM_SLOT = bars + 112;
     volatile uint32_t* tmem_ptr_sm = reinterpret_cast<volatile uint32_t*>(smem_raw + (TMEM_SLOT - smem_u32(smem_raw)));
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CH_BN >> 3) << 17) | ((uint32_t)(SDF_BM >> 4) << 24);
     const unsigned nctas = gridDim.x;
+    const int NT = H / CH_BN;                                  // column tiles = clusters
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < CH_STAGES; s++) { mbar_init(BAR_F + 8 * s, 1); mbar_init(BAR_E + 8 * s, 1); }
-        mbar_init(BAR_TF, 1); mbar_init(BAR_SD, 4);
-        mbar_init(BAR_RDY, SK_SPLIT); mbar_init(BAR_FREE, SK_SPLIT);
+        for (int b2 = 0; b2 < 2; b2++) { mbar_init(BAR_TF + 8 * b2, 1); mbar_init(BAR_SD + 8 * b2, 4); }
+        mbar_init(BAR_RDY, SK_SPLIT); mbar_init(BAR_CONS, SK_SPLIT);
+        for (int b2 = 0; b2 < 2; b2++) { mbar_init(BAR_ST + 8 * b2, 1); mbar_init(BAR_STA + 8 * b2, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -577,14 +593,21 @@ k_sdf_chain_sk(SkChain c, int H, int m_rows, const int* __restrict__ m_count) {
                 const float* xhi = c.act[l & 1][0];
                 const float* xlo = c.act[l & 1][1];
                 for (int mb = 0; mb < row_blocks; mb++) {
-                    const bool first = (mb == 0 && l > 0);
+                    const bool first = l > 0;
+                    CH_T(l * row_blocks + mb, 0);
                     if (first) {
                         for (int j = 0; j < npre; j++) issue_w(l, j, it + (uint32_t)j);      // independent of the activations
-                        const unsigned need = (unsigned)l * nctas;                            // layer l - 1 is complete device-wide
-                        unsigned seen;
-                        do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(c.sync) : "memory"); } while (seen < need);
+                        // this rank's K slice of row-block mb = columns [32 k0, 32 (k0 + kbs)) of layer l - 1: wait for the column tiles holding them
+                        const int t_lo = (32 * k0) / CH_BN, t_hi = (32 * (k0 + kbs) - 1) / CH_BN;
+                        const unsigned need = (unsigned)l * SK_SPLIT;                         // 8 CTAs of the owning cluster, l layers so far
+                        for (int t = t_lo; t <= t_hi; t++) {
+                            const unsigned* cnt = c.sync + 2 + (size_t)mb * NT + t;
+                            unsigned seen;
+                            do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory"); } while (seen < need);
+                        }
                         asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes of the other CTAs before this CTA's bulk copies
                     }
+                    CH_T(l * row_blocks + mb, 1);
                     for (int kb = 0; kb < kbs; kb++, it++) {
                         if (!(first && kb < npre)) issue_w(l, kb, it);
                         const uint32_t s = it % CH_STAGES;
@@ -594,6 +617,7 @@ k_sdf_chain_sk(SkChain c, int H, int m_rows, const int* __restrict__ m_count) {
                         tma_bulk_g2s(st, xhi + oa, SDF_TILE_BYTES, full);
                         tma_bulk_g2s(st + SDF_TILE_BYTES, xlo + oa, SDF_TILE_BYTES, full);
                     }
+                    CH_T(l * row_blocks + mb, 2);
                 }
             }
         }
@@ -603,13 +627,17 @@ k_sdf_chain_sk(SkChain c, int H, int m_rows, const int* __restrict__ m_count) {
             int tile = 0;
             for (int l = 0; l < nl; l++) {
                 for (int mb = 0; mb < row_blocks; mb++, tile++) {
-                    if (tile > 0) {                                      // the epilogue has drained the accumulator of the previous tile
-                        mbar_wait(BAR_SD, (uint32_t)(tile - 1) & 1);
+                    const uint32_t ab = (uint32_t)tile & 1;              // accumulator buffer of this tile
+                    const uint32_t acc = tmem_acc + ab * CH_BN;
+                    if (tile > 1) {                                      // the epilogue has drained this buffer (tile - 2)
+                        mbar_wait(BAR_SD + 8 * ab, (uint32_t)((tile >> 1) - 1) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     }
                     for (int kb = 0; kb < kbs; kb++, it++) {
                         const uint32_t s = it % CH_STAGES, ph = (it / CH_STAGES) & 1;
                         mbar_wait(BAR_F + 8 * s, ph);
+                        if (kb == 0) CH_T(tile, 3);
+                        if (kb == kbs - 1) CH_T(tile, 4);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t as = base + s * CH_STAGE_BYTES, ws = as + 2 * SDF_TILE_BYTES;
 #pragma unroll
@@ -617,23 +645,45 @@ k_sdf_chain_sk(SkChain c, int H, int m_rows, const int* __restrict__ m_count) {
                             const uint32_t ko = ks * 256;
                             const uint64_t ahi = umma_desc(as + ko), alo = umma_desc(as + SDF_TILE_BYTES + ko);
                             const uint64_t bhi = umma_desc(ws + ko), blo = umma_desc(ws + SDF_TILE_BYTES + ko);
-                            umma_tf32(tmem_acc, alo, bhi, idesc, (kb | ks) ? 1u : 0u);
-                            umma_tf32(tmem_acc, ahi, blo, idesc, 1u);
-                            umma_tf32(tmem_acc, ahi, bhi, idesc, 1u);
+                            umma_tf32(acc, alo, bhi, idesc, (kb | ks) ? 1u : 0u);
+                            umma_tf32(acc, ahi, blo, idesc, 1u);
+                            umma_tf32(acc, ahi, bhi, idesc, 1u);
                         }
                         umma_commit(BAR_E + 8 * s);
                     }
-                    umma_commit(BAR_TF);
+                    umma_commit(BAR_TF + 8 * ab);
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // publisher: makes a finished tile visible device-wide and counts it in, off the epilogue's critical path.  The epilogue threads'
+        // global stores happen-before its fence through the CTA barrier + mbarrier (release / acquire), the fence is cumulative.
+        if (lane == 0) {
+            int tile = 0;
+            for (int l = 0; l + 1 < nl; l++) {
+                for (int mb = 0; mb < row_blocks; mb++, tile++) {
+                    const uint32_t sb = (uint32_t)tile & 1;
+                    mbar_wait(BAR_ST + 8 * sb, (uint32_t)(tile >> 1) & 1);
+                    __threadfence();
+                    asm volatile("fence.proxy.async;" ::: "memory");
+                    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(c.sync + 2 + (size_t)mb * NT + nb), "r"(1u) : "memory");
+                    mbar_arrive(BAR_STA + 8 * sb);
                 }
             }
         }
     } else {
+        // epilogue.  Split-K reduce-scatter by PUSH: every CTA drains its 128 x 128 partial accumulator from TMEM and stores the 16 columns
+        // that rank d finishes straight into rank d's shared memory (st.shared::cluster: posted writes, no round trip), slab [source rank];
+        // after the cluster-wide "pushed" barrier each CTA sums its 8 slabs locally in fixed rank order (deterministic; the order of
+        // k_sdf_gemm_sk: bit-identical results).  Pulling the slices with ld.shared::cluster instead cost 3.5 us per tile.
         const int q = warp & 3;
         const int rl = 32 * q + lane;                               // row inside the 128-row block = TMEM lane
         const int et = threadIdx.x - 64;                            // 0..127 among the epilogue threads
         const size_t row_off = (size_t)(rl >> 3) * 256 + (rl & 7) * 4;
         const int col0 = nb * CH_BN + 16 * (int)rank;               // the 16 output columns this CTA finishes
         const size_t out_off = (size_t)(col0 / SDF_BK) * SDF_TILE_FLOATS + (size_t)((col0 % SDF_BK) / 4) * 32 + row_off;
+        // slab of source rank r, column group g (4 columns), row: ((r * 4 + g) * 128 + row) * 16 bytes inside the 64 KB staging area
+        const uint32_t my_slab = stg_sm + (uint32_t)((rank * 4) * SDF_BM + rl) * 16u;     // where THIS rank's values land in a destination CTA
         int tile = 0;
         for (int l = 0; l < nl; l++) {
             float bv[16];
@@ -645,38 +695,49 @@ k_sdf_chain_sk(SkChain c, int H, int m_rows, const int* __restrict__ m_count) {
             float* yhi = c.act[(l + 1) & 1][0];
             float* ylo = c.act[(l + 1) & 1][1];
             for (int mb = 0; mb < row_blocks; mb++, tile++) {
-                const uint32_t par = (uint32_t)tile & 1;
-                mbar_wait(BAR_TF, par);                                 // every MMA of this tile has retired: the accumulator is complete
+                const uint32_t par = (uint32_t)tile & 1;                // phase of the cluster barriers (one use per tile)
+                const uint32_t ab = (uint32_t)tile & 1;                 // accumulator buffer
+                if (et == 0) CH_T(tile, 5);
+                mbar_wait(BAR_TF + 8 * ab, (uint32_t)(tile >> 1) & 1);  // every MMA of this tile has retired: the accumulator is complete
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (tile > 0) mbar_wait_cluster(BAR_CONS, (uint32_t)(tile - 1) & 1);   // every destination has summed the previous tile's slabs
+                if (et == 0) CH_T(tile, 6);
 #pragma unroll 1
                 for (int cc = 0; cc < CH_BN; cc += 32) {
                     uint32_t v[32];
-                    tmem_ld32(tmem_acc + ((uint32_t)(32 * q) << 16) + (uint32_t)cc, v);
+                    tmem_ld32(tmem_acc + ((uint32_t)(32 * q) << 16) + ab * CH_BN + (uint32_t)cc, v);
 #pragma unroll
-                    for (int c4 = 0; c4 < 8; c4++)                      // staging[column / 4][row][4]: consecutive lanes -> consecutive 16-byte words
-                        st_smem_f4(stg_sm + (uint32_t)(((cc >> 2) + c4) * SDF_BM + rl) * 16u, __uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]),
-                                   __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
+                    for (int h2 = 0; h2 < 2; h2++) {                    // columns [cc + 16 h2, + 16) belong to rank cc / 16 + h2
+                        const uint32_t dst = mapa_u32(my_slab, (uint32_t)(cc >> 4) + h2);
+#pragma unroll
+                        for (int g = 0; g < 4; g++)
+                            asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)g * SDF_BM * 16u),
+                                         "f"(__uint_as_float(v[16 * h2 + 4 * g])), "f"(__uint_as_float(v[16 * h2 + 4 * g + 1])),
+                                         "f"(__uint_as_float(v[16 * h2 + 4 * g + 2])), "f"(__uint_as_float(v[16 * h2 + 4 * g + 3])) : "memory");
+                    }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 asm volatile("fence.acq_rel.cluster;" ::: "memory");
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et < SK_SPLIT) mbar_arrive_remote(mapa_u32(BAR_RDY, (uint32_t)et));
-                if (lane == 0) mbar_arrive(BAR_SD);                     // TMEM has been read: the next tile's MMAs may overwrite it
-                mbar_wait_cluster(BAR_RDY, par);                        // all 8 partial tiles are in shared memory
+                if (et < SK_SPLIT) mbar_arrive_remote(mapa_u32(BAR_RDY, (uint32_t)et));     // "my slab is in your staging area"
+                if (lane == 0) mbar_arrive(BAR_SD + 8 * ab);            // this accumulator has been read: tile + 2 may overwrite it
+                if (et == 0) CH_T(tile, 7);
+                mbar_wait_cluster(BAR_RDY, par);                        // all 8 slabs have landed here
+                if (et == 0) CH_T(tile, 8);
                 float acc[16];
 #pragma unroll
                 for (int e = 0; e < 16; e++) acc[e] = 0.f;
 #pragma unroll
                 for (uint32_t r = 0; r < SK_SPLIT; r++) {               // fixed order: deterministic
-                    const uint32_t ra = mapa_u32(stg_sm + (uint32_t)((4 * rank) * SDF_BM + rl) * 16u, r);
 #pragma unroll
                     for (int g = 0; g < 4; g++) {
-                        const float4 a = ld_dsmem_f4(ra + (uint32_t)g * SDF_BM * 16u);
+                        float4 a;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w)
+                                     : "r"(stg_sm + (uint32_t)((r * 4 + g) * SDF_BM + rl) * 16u) : "memory");
                         acc[4 * g] += a.x; acc[4 * g + 1] += a.y; acc[4 * g + 2] += a.z; acc[4 * g + 3] += a.w;
                     }
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");          // all reads of the peers' tiles are done
-                if (et < SK_SPLIT) mbar_arrive_remote(mapa_u32(BAR_FREE, (uint32_t)et));
+                if (et == 0) CH_T(tile, 9);
                 float* dh = yhi + (size_t)mb * KB * SDF_TILE_FLOATS + out_off;
                 float* dl = ylo + (size_t)mb * KB * SDF_TILE_FLOATS + out_off;
 #pragma unroll
@@ -690,17 +751,16 @@ k_sdf_chain_sk(SkChain c, int H, int m_rows, const int* __restrict__ m_count) {
                     *reinterpret_cast<float4*>(dh + 32 * g) = make_float4(h[0], h[1], h[2], h[3]);
                     *reinterpret_cast<float4*>(dl + 32 * g) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                 }
-                mbar_wait_cluster(BAR_FREE, par);                       // no peer still reads this CTA's partial tile: it may be overwritten
-            }
-            if (l + 1 < nl) {
-                // device-wide barrier, arrive side: this CTA's share of the layer's activations is written and visible
-                __threadfence();
-                asm volatile("fence.proxy.async;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (et == 0) {
-                    __threadfence();
-                    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(c.sync), "r"(1u) : "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");          // staging read by everyone here; this tile's global stores are issued
+                if (et < SK_SPLIT) mbar_arrive_remote(mapa_u32(BAR_CONS, (uint32_t)et));    // "I have summed your slab": the source may push again
+                if (et == 0 && l + 1 < nl) {
+                    // hand the tile to the publisher warp (two tiles may be pending: double-buffered handshake)
+                    const uint32_t sb = (uint32_t)tile & 1;
+                    if (tile > 1) mbar_wait(BAR_STA + 8 * sb, (uint32_t)((tile >> 1) - 1) & 1);
+                    mbar_arrive(BAR_ST + 8 * sb);
                 }
+                if (et == 0) CH_T(tile, 10);
+                if (et == 0) CH_T(tile, 11);
             }
         }
     }
@@ -712,8 +772,12 @@ k_sdf_chain_sk(SkChain c, int H, int m_rows, const int* __restrict__ m_count) {
     }
     if (threadIdx.x == 0) {
         // every CTA has passed its last barrier wait before it gets here: the last one out re-arms the counters
-        const unsigned old = atomicAdd(c.sync + 1, 1u);
-        if (old == nctas - 1) { c.sync[0] = 0u; c.sync[1] = 0u; __threadfence(); }
+        const unsigned old = atomicAdd(c.sync, 1u);
+        if (old == nctas - 1) {
+            for (int k = 0; k < row_blocks * NT; k++) c.sync[2 + k] = 0u;
+            c.sync[0] = 0u;
+            __threadfence();
+        }
     }
 }
 

@@ -79,6 +79,14 @@ inline cudaError_t sdf_reserve(MisSdf* s, int rows) {
     }
     e = cudaMalloc((void**)&s->vals, (size_t)4 * need * sizeof(float));
     if (e != cudaSuccess) return e;
+    // arrival counters of the one-launch chain: one per (row-block, column tile) + 2
+    if (s->chain_sync) cudaFree(s->chain_sync);
+    s->chain_sync = nullptr;
+    const size_t nsync = 2 + (size_t)(need / 128) * (size_t)((s->H + CH_BN - 1) / CH_BN);
+    e = cudaMalloc((void**)&s->chain_sync, nsync * sizeof(unsigned));
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(s->chain_sync, 0, nsync * sizeof(unsigned));
+    if (e != cudaSuccess) return e;
     s->cap = need;
     return cudaSuccess;
 }
@@ -120,7 +128,7 @@ inline cudaError_t sdf_forward(MisSdf* s, const float* pts, const int* idx, int 
         c.W = s->Wslab; c.bias = s->bslab; c.n_layers = (int)s->Whi.size(); c.sync = s->chain_sync;
         for (int b = 0; b < 2; b++) for (int h = 0; h < 2; h++) c.act[b][h] = s->act[b][h];
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((H / CH_BN) * SK_SPLIT); cfg.blockDim = dim3(SDF_THREADS); cfg.dynamicSmemBytes = CH_SMEM_BYTES; cfg.stream = st;
+        cfg.gridDim = dim3((H / CH_BN) * SK_SPLIT); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = CH_SMEM_BYTES; cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
         cfg.attrs = at; cfg.numAttrs = 1;

@@ -92,6 +92,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // K-major, no swizzle: LBO = 128 B between core matrices along K, SBO = 1024 B between 8-row groups, descriptor version 1
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3fffu) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46);
@@ -664,9 +676,8 @@ k_sdf_chain_sk(SkChain c, int H, int m_rows, const int* __restrict__ m_count) {
                 for (int mb = 0; mb < row_blocks; mb++, tile++) {
                     const uint32_t sb = (uint32_t)tile & 1;
                     mbar_wait(BAR_ST + 8 * sb, (uint32_t)(tile >> 1) & 1);
-                    __threadfence();
                     asm volatile("fence.proxy.async;" ::: "memory");
-                    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(c.sync + 2 + (size_t)mb * NT + nb), "r"(1u) : "memory");
+                    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(c.sync + 2 + (size_t)mb * NT + nb), "r"(1u) : "memory");   // release: cumulative over the tile's stores
                     mbar_arrive(BAR_STA + 8 * sb);
                 }
             }
@@ -702,18 +713,22 @@ k_sdf_chain_sk(SkChain c, int H, int m_rows, const int* __restrict__ m_count) {
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (tile > 0) mbar_wait_cluster(BAR_CONS, (uint32_t)(tile - 1) & 1);   // every destination has summed the previous tile's slabs
                 if (et == 0) CH_T(tile, 6);
-#pragma unroll 1
-                for (int cc = 0; cc < CH_BN; cc += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_acc + ((uint32_t)(32 * q) << 16) + ab * CH_BN + (uint32_t)cc, v);
 #pragma unroll
-                    for (int h2 = 0; h2 < 2; h2++) {                    // columns [cc + 16 h2, + 16) belong to rank cc / 16 + h2
+                for (int cc = 0; cc < CH_BN; cc += 64) {                // two 32-column loads in flight per wait
+                    uint32_t v[32], v2[32];
+                    tmem_ld32_nowait(tmem_acc + ((uint32_t)(32 * q) << 16) + ab * CH_BN + (uint32_t)cc, v);
+                    tmem_ld32_nowait(tmem_acc + ((uint32_t)(32 * q) << 16) + ab * CH_BN + (uint32_t)cc + 32u, v2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int h2 = 0; h2 < 4; h2++) {                    // columns [cc + 16 h2, + 16) belong to rank cc / 16 + h2
+                        const uint32_t* vv = h2 < 2 ? v : v2;
+                        const int hh = h2 & 1;
                         const uint32_t dst = mapa_u32(my_slab, (uint32_t)(cc >> 4) + h2);
 #pragma unroll
                         for (int g = 0; g < 4; g++)
                             asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + (uint32_t)g * SDF_BM * 16u),
-                                         "f"(__uint_as_float(v[16 * h2 + 4 * g])), "f"(__uint_as_float(v[16 * h2 + 4 * g + 1])),
-                                         "f"(__uint_as_float(v[16 * h2 + 4 * g + 2])), "f"(__uint_as_float(v[16 * h2 + 4 * g + 3])) : "memory");
+                                         "f"(__uint_as_float(vv[16 * hh + 4 * g])), "f"(__uint_as_float(vv[16 * hh + 4 * g + 1])),
+                                         "f"(__uint_as_float(vv[16 * hh + 4 * g + 2])), "f"(__uint_as_float(vv[16 * hh + 4 * g + 3])) : "memory");
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

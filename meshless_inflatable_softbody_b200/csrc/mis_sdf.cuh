@@ -781,6 +781,11 @@ k_sdf_chain_sk(SkChain c, int H, int m_rows, const int* __restrict__ m_count) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    // No CTA may leave while a peer can still touch its shared memory: after the last tile the destinations still arrive on this CTA's
+    // "consumed" barrier (remote mbarrier arrive) once they have summed its slab.  Leaving early is an access to the shared memory of an
+    // exited CTA -- a sporadic launch failure under load.  The cluster barrier closes the window.
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"((uint32_t)CH_TMEM_COLS) : "memory");

@@ -251,7 +251,7 @@ def size_cpu_sample(cfg, n_full, total_steps, budget_s):
 def run_reference(args, cfg, rank, world):
     if rank != 0:
         return
-    n_s, _ = size_cpu_sample(cfg, args.n, args.steps + args.warmup, budget_s=60.0)
+    n_s, _ = size_cpu_sample(cfg, args.n, args.steps + args.warmup, budget_s=args.ref_budget)
     rate, dt, cores, n_used, dt_mlp = cpu_faithful_rate(cfg, n_s, args.steps, args.warmup)
     sample = (f"{args.steps} steps (+{args.warmup} warm-up) of a {n_used}-particle sphere, same spacing/params as the GPU workload, "
               f"oracle FAITHFUL mode (27-cell walk, per-candidate svd3) on {cores} OpenMP threads + the 9x1024 MLP on 1% of the "
@@ -496,6 +496,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=60.0, help="--impl reference: seconds of CPU work the sample is sized for")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.n <= 0:

@@ -167,3 +167,28 @@ def test_push_plan_fills_every_ghost_slot_once(world, tmp_path):
     port = 31500 + (os.getpid() % 2000) + world
     mp.spawn(_push_worker, args=(world, x0, port, str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok_{r}.npy").exists() for r in range(world))
+
+
+def test_plan_invariants_on_a_regular_lattice_with_ties():
+    """An un-jittered lattice puts whole planes of particles on one coordinate: a cut falls on a tie.  Ownership stays a partition,
+    ghost layers still cover the neighbourhoods, and particles exactly 2h from a cut (not neighbours of anything across it: the
+    support test is strict, sim.py:139-141) may or may not be ghosts without harm."""
+    s = 0.5 * H
+    ax = np.arange(40) * s
+    ay = np.arange(9) * s
+    x0 = np.stack(np.meshgrid(ax, ay, ay, indexing="ij"), -1).reshape(-1, 3).astype(np.float32) + np.float32([0.0, 0.05, 0.0])
+    for world in (2, 3):
+        part = SlabPartition.build(x0, H, world)
+        owned_all = np.concatenate([p.owned for p in part.plans])
+        assert np.array_equal(np.sort(owned_all), np.arange(len(x0)))
+        nb = _neighbours(x0)
+        for p in part.plans:
+            local = set(p.local_ids.tolist())
+            layer1 = set(p.ghosts[p.ghost_layer == 1].tolist())
+            owned_set = set(p.owned.tolist())
+            for i in p.owned[:: max(1, len(p.owned) // 300)]:
+                assert all((j in owned_set) or (j in layer1) for j in nb[i])
+            for i in list(layer1)[:: max(1, len(layer1) // 300)]:
+                assert all(j in local for j in nb[i])
+            for q, ids in p.recv.items():
+                assert np.array_equal(p.local_ids[ids], part.plans[q].owned[part.plans[q].send[p.rank]])

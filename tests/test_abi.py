@@ -67,3 +67,20 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("the oracle's", "").replace("oracle's", "").lower() or f.endswith((".cu", ".cuh")), f
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_integration_stub_mirrors_the_params_struct():
+    """The ctypes stub shown to a maintainer in INTEGRATION.md lists the MisParams fields in the header's order, and every entry
+    point its tables name is declared in include/mis.h."""
+    from meshless_inflatable_softbody_b200 import native
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class MisParams\(C\.Structure\):.*?_fields_ = (.*?)\n\nmis = ", doc, re.S)
+    assert m, "the MisParams stub moved"
+    names = re.findall(r'"([a-z_0-9]+)"', m.group(1))
+    assert names == [n for n, _ in native.MisParams._fields_]
+    declared = set(_declared())
+    mentioned = set(re.findall(r"`(mis_[a-z0-9_]+)", doc))
+    wild = {n for n in mentioned if n.endswith("_")}                      # families written as `mis_halo_*`
+    assert (mentioned - wild) <= declared, sorted((mentioned - wild) - declared)
+    for w in wild:
+        assert any(d.startswith(w) for d in declared), w

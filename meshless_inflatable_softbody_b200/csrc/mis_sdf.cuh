@@ -504,8 +504,9 @@ k_sdf_gemm_sk(const float* __restrict__ Xhi, const float* __restrict__ Xlo, cons
 // k_sdf_gemm_sk pays a launch, a pipeline fill and a drain per layer; at a few hundred rows those fixed latencies are the whole cost
 // (7 layers x ~14 us per pass of the per-step contact query).  k_sdf_chain_sk walks every hidden layer inside one launch:
 //   * decomposition: cluster c (8 CTAs) owns output columns [128 c, 128 c + 128), CTA rank r the K slice [K r / 8, K (r + 1) / 8)
-//     (split-K); the 8 partial 128 x 128 accumulators go TMEM -> shared memory and are reduced through distributed shared memory in
-//     FIXED rank order (deterministic, and the same order as k_sdf_gemm_sk: bit-identical results); rank r finishes 16 columns.
+//     (split-K); every CTA PUSHES the 16 columns of its partial 128 x 128 accumulator that rank d finishes from TMEM straight into
+//     rank d's shared memory (st.shared::cluster), and each CTA then sums its 8 slabs locally in FIXED rank order (deterministic, and
+//     the same order as k_sdf_gemm_sk: bit-identical results).  Pulling the slices with ld.shared::cluster cost 3.5 us per tile.
 //     H / 128 clusters = 64 CTAs at H = 1024: a cooperative launch accepts at most 15 co-resident 8-CTA clusters on a B200 (measured:
 //     cudaOccupancyMaxActiveClusters), which rules out the 16 clusters of 64-column tiles;
 //   * dependencies between layers are tracked per (row-block, column tile): the K slice a CTA reads is produced by the CTAs of the
@@ -514,14 +515,16 @@ k_sdf_gemm_sk(const float* __restrict__ Xhi, const float* __restrict__ Xlo, cons
 //     at a device-wide barrier.  Cooperative launch => all CTAs are co-resident, the waits cannot deadlock.  The two ping-pong
 //     activation buffers stay safe: a column tile of a row-block is overwritten (layer l + 1) only after the whole writing cluster
 //     holds the layer-l outputs of ALL clusters for that row-block, i.e. after every reader of the old contents has finished;
-//   * the W tiles of the next layer's first k-blocks do not depend on the activations: they are issued into the ring BEFORE the barrier
-//     wait (same stage barrier; the A halves complete the transaction count afterwards);
-//   * the partial tile has its own 64 KB of shared memory and the accumulator is double-buffered in TMEM (2 x 128 columns), so loads and
-//     MMAs of the next tile run under the drain / reduce / store of the current one.
+//   * the W tiles of the next layer's first k-blocks do not depend on the activations: they are issued into the ring BEFORE the
+//     dependency wait (same stage barrier; the A halves complete the transaction count afterwards);
+//   * the slabs have their own 64 KB of shared memory and the accumulator is double-buffered in TMEM (2 x 128 columns), so loads and
+//     MMAs of the next tile run under the drain / push / sum / store of the current one; a seventh warp publishes finished tiles
+//     (release add on the dependency counter), which keeps the wait for the global stores off the epilogue's path;
+//   * the kernel ends with a cluster barrier: no CTA may exit while a peer can still arrive on one of its barriers.
 constexpr int CH_BN = 128;
 constexpr int CH_STAGES = 2;
 constexpr int CH_STAGE_BYTES = 4 * SDF_TILE_BYTES;                         // A_hi, A_lo, W_hi, W_lo of one k-block: 64 KB
-constexpr int CH_STAGING_BYTES = SDF_BM * CH_BN * 4;                       // 64 KB fp32 partial tile
+constexpr int CH_STAGING_BYTES = SDF_BM * CH_BN * 4;                       // 64 KB: 8 slabs (one per source rank) of 128 rows x 16 columns fp32
 constexpr int CH_TMEM_COLS = 256;                                         // two 128-column accumulators: the MMAs of tile t + 1 run while tile t is drained
 constexpr int CH_SMEM_BYTES = CH_STAGES * CH_STAGE_BYTES + CH_STAGING_BYTES + 256 + 1024;
 constexpr int CH_THREADS = SDF_THREADS + 32;                             // + one warp that publishes finished tiles (fence + release) off the epilogue's path

@@ -1,5 +1,5 @@
 // mis_api.cu -- the C-ABI of include/mis.h: owns the cell-sorted structure-of-arrays
-// state of one scene and enqueues the kernels of mis_neighbors.cuh / mis_step.cuh.
+// state of one scene and enqueues the kernels of mis_sort.cuh, mis_neighbors.cuh, mis_cluster.cuh and mis_sdf.cuh.
 #include "../../include/mis.h"
 #include "mis_math.cuh"
 #include "mis_neighbors.cuh"

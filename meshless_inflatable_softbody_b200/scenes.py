@@ -78,3 +78,47 @@ def shell_mask(x0: np.ndarray, h: float, centre=None):
     c = x0.mean(0) if centre is None else np.asarray(centre)
     r = np.linalg.norm(x0 - c, axis=1)
     return r > r.max() - 2 * h
+
+
+def plateau_obstacle_state(radius: float, y_top: float, hidden: int = 1024, n_linear: int = 9):
+    """State dict (the reference's DeepSDFWithCode keys, deepsdf.py:12-38) of a ReLU MLP that computes EXACTLY
+
+        sdf(p) = max( (|x| + |y| + |z| - radius) / sqrt(3),  y - y_top ),
+
+    an octahedron whose upper tip is cut off by the plane y = y_top: a flat square plateau |x| + |z| <= radius - y_top
+    a soft body can rest on, so a contact patch holds tens to hundreds of particles (a sharp tip holds a handful).
+    Layer 0: relu(+-x), relu(+-y), relu(+-z); layer 1: c = relu(a - b), and y+ = relu(y), y- = relu(-y) passed through;
+    hidden layers pass (c, y+, y-) through; the last layer returns c + y+ - y- - y_top = b + relu(a - b) = max(a, b).
+    Every Linear is weight-normalised (W = g v / |v| per row): v = the row, g = its norm (g = 0 silences a row)."""
+    if n_linear < 3:
+        raise ValueError("needs at least one hidden-to-hidden layer")
+    dims = [3] + [hidden] * (n_linear - 1) + [1]
+    st = {}
+    k = 1.0 / np.sqrt(3.0)
+    for l in range(n_linear):
+        o, i = dims[l + 1], dims[l]
+        W = np.zeros((o, i), np.float64)
+        b = np.zeros(o, np.float64)
+        if l == 0:
+            for a in range(3):
+                W[2 * a, a] = 1.0; W[2 * a + 1, a] = -1.0
+        elif l == 1:
+            W[0, :6] = k; W[0, 2] = k - 1.0; W[0, 3] = k + 1.0; b[0] = y_top - radius * k
+            W[1, 2] = 1.0; W[2, 3] = 1.0
+        elif l < n_linear - 1:
+            for u in range(3):
+                W[u, u] = 1.0
+        else:
+            W[0, 0] = 1.0; W[0, 1] = 1.0; W[0, 2] = -1.0; b[0] = -y_top
+        g = np.sqrt((W * W).sum(1, keepdims=True))
+        v = W.copy()
+        v[g[:, 0] == 0.0, 0] = 1.0            # keep |v| non-zero; g = 0 silences the row
+        st[f"network.{3 * l}.parametrizations.weight.original0"] = g.astype(np.float32)
+        st[f"network.{3 * l}.parametrizations.weight.original1"] = v.astype(np.float32)
+        st[f"network.{3 * l}.bias"] = b.astype(np.float32)
+    return st
+
+
+def plateau_obstacle_bbox(radius: float, y_top: float, margin: float):
+    """(min xyz, max xyz) of the region where the plateau obstacle's sdf can be below `margin`."""
+    return [-radius - margin, -radius - margin, -radius - margin, radius + margin, y_top + margin, radius + margin]

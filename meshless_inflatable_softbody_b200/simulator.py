@@ -71,15 +71,29 @@ class Simulator:
     def _st(self):
         return C.c_void_p(self.stream.cuda_stream)
 
-    def _dev(self, a, shape):
-        """Broadcast a scalar / sequence / array / tensor to a contiguous fp32 device tensor."""
+    def _dev(self, a, shape, own: bool = False):
+        """Broadcast a scalar / sequence / array / tensor to a contiguous fp32 device tensor the library's stream may read.
+
+        own=True returns a private copy (the setters keep it).  Every kernel that produces the tensor (conversion, expand,
+        clone) is enqueued on torch's current stream BEFORE the library stream is made to wait for that stream, and the
+        tensor is recorded on the library stream so the caching allocator does not hand its memory out again while a
+        library kernel still reads it (torch streams are non-blocking: nothing else orders the two)."""
         if isinstance(a, torch.Tensor):
             t = a.to(device=self.device, dtype=torch.float32)
         else:
             t = torch.as_tensor(np.asarray(a, dtype=np.float32), device=self.device)
         t = t.expand(shape).contiguous()
-        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        if own and isinstance(a, torch.Tensor) and t.data_ptr() == a.data_ptr():
+            t = t.clone()
+        self._publish(t)
         return t
+
+    def _publish(self, *tensors):
+        """Order the library stream after everything enqueued so far on torch's current stream; keep `tensors` alive for it."""
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        for t in tensors:
+            if t is not None and t.is_cuda:
+                t.record_stream(self.stream)
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -98,16 +112,17 @@ class Simulator:
 
     # ------------------------------------------------------------------ control functions (sim.py:279-308)
     def set_all_external_force(self, f: Sequence[float]):
-        self._fext = self._dev(f, (self.n, 3)).clone()
+        self._fext = self._dev(f, (self.n, 3), own=True)
         native.check(self.L.mis_set_ext_force(self._h, self._fext.data_ptr(), self._st()), "mis_set_ext_force")
 
     def set_external_force(self, i, f):
         """sim.py:279-280; i may be an index or an index array."""
         self._fext[i] = torch.as_tensor(np.asarray(f, np.float32), device=self.device)
+        self._publish(self._fext)
         native.check(self.L.mis_set_ext_force(self._h, self._fext.data_ptr(), self._st()), "mis_set_ext_force")
 
     def set_external_forces(self, f):
-        self._fext = self._dev(f, (self.n, 3)).clone()
+        self._fext = self._dev(f, (self.n, 3), own=True)
         native.check(self.L.mis_set_ext_force(self._h, self._fext.data_ptr(), self._st()), "mis_set_ext_force")
 
     def set_external_forces_host(self, f_host: torch.Tensor):
@@ -119,26 +134,26 @@ class Simulator:
         if not hasattr(self, "_free"):
             self._free = torch.ones((self.n, 3), device=self.device, dtype=torch.float32)
         self._free[i] = torch.as_tensor(np.asarray(d, np.float32), device=self.device)
-        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        self._publish(self._free)
         native.check(self.L.mis_set_dirichlet(self._h, self._free.data_ptr(), self._st()), "mis_set_dirichlet")
 
     def set_youngs_modulus(self, E):
-        self._E = self._dev(E, (self.n,)).clone()
+        self._E = self._dev(E, (self.n,), own=True)
         if hasattr(self, "_nu"):
             native.check(self.L.mis_set_material(self._h, self._E.data_ptr(), self._nu.data_ptr(), self._st()), "mis_set_material")
 
     def set_poisson_ratio(self, nu):
-        self._nu = self._dev(nu, (self.n,)).clone()
+        self._nu = self._dev(nu, (self.n,), own=True)
         if hasattr(self, "_E"):
             native.check(self.L.mis_set_material(self._h, self._E.data_ptr(), self._nu.data_ptr(), self._st()), "mis_set_material")
 
     def set_mass(self, m):
-        self._m = self._dev(m, (self.n,)).clone()
+        self._m = self._dev(m, (self.n,), own=True)
         native.check(self.L.mis_set_mass(self._h, self._m.data_ptr(), self._st()), "mis_set_mass")
 
     def set_design(self, x):
         """x -> ratio = 0.5 tanh(k x) + 0.5 (compute_ratio, sim.py:107-110)."""
-        self._x = self._dev(x, (self.n,)).clone()
+        self._x = self._dev(x, (self.n,), own=True)
         native.check(self.L.mis_set_design(self._h, self._x.data_ptr(), self._st()), "mis_set_design")
 
     # ------------------------------------------------------------------ rollout (sim.py:341-358)
@@ -402,6 +417,10 @@ class Simulator:
         native.check(self.L.mis_profile_step(self._h, int(n_steps), self._st(), C.byref(a), C.byref(b)), "mis_profile_step")
         self.frame += int(n_steps)
         return a.value, b.value
+
+    def kernel_names(self):
+        """Names of the two gather kernels the step launches (what profile_step times; keys of profiles/traffic.json)."""
+        return {"k_deform": "k_deform_c", "k_force": "k_force_c"}
 
     @property
     def launch_count(self) -> int:

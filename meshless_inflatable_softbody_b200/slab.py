@@ -248,6 +248,7 @@ class SlabSimulator:
         local = self.plan.local_ids
         self.sim = Simulator(x0_global[local], self.cfg, device=device, **sim_kw)
         self.n_owned = self.plan.n_owned
+        self._x0_owned = x0_global[self.plan.owned]
         if len(self.plan.ghosts):
             ghost_local = torch.arange(self.n_owned, len(local), device=self.device)
             self.sim.set_dirichlet(ghost_local, [0.0, 0.0, 0.0])        # ghosts move only through the exchange
@@ -357,6 +358,19 @@ class SlabSimulator:
         self.sim.set_mass(m)
         if self.world > 1 and not self.in_process:
             self._exchange_volumes()
+
+    def set_sdf_obstacle(self, sdf, bbox_model, xform=None, fd_eps: float = 1e-3):
+        """Per-step obstacle contact for this rank's particles (Simulator.set_sdf_obstacle).  Contact is local to a particle
+        (no neighbour sum), so no exchange is added; the force of a ghost is never used (its owner integrates it)."""
+        self.sim.set_sdf_obstacle(sdf, bbox_model, xform=xform, fd_eps=fd_eps)
+
+    def obstacle_nearby(self, bbox_world, margin: float) -> bool:
+        """True if any OWNED particle's reference position lies within `margin` of the world-space box (min xyz, max xyz).
+        A rank for which this is False, with `margin` above the distance the body travels during the run, can skip the
+        per-step obstacle query altogether (slab-level broad phase; the partition is static)."""
+        bb = np.asarray(bbox_world, np.float64).reshape(2, 3)
+        x0 = self._x0_owned
+        return bool(np.any(np.all((x0 >= bb[0] - margin) & (x0 <= bb[1] + margin), axis=1)))
 
     def startup(self, v0=None):
         if self.halo == "p2p" and self.world > 1 and not self.in_process:

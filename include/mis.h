@@ -195,6 +195,20 @@ int mis_eval_forces(MisSim* sim, const float* x_dev, float* fel_dev, void* strea
  * at the current frame; targets are n*3 fp32 in caller order (the position_{i}.npy / velocity_{i}.npy of sim.py:118-119).
  * Deterministic (fixed summation order).  The reverse pass (wp.Tape, sim.py:346-372) is out of scope.                       */
 int mis_accumulate_loss(MisSim* sim, const float* target_x_dev, const float* target_v_dev, double* loss_dev, void* stream);
+/* Gather mode of the two per-step neighbour-gather kernels (compute_A_pq / compute_nabla_u / compute_elastic_forces,
+ * sim.py:170-235; same results to the fp32 summation-order floor):
+ *   0  both passes: register-tiled clusters of 2 particles streaming a union neighbour list from global memory
+ *      (k_deform_c, k_force_c)
+ *   1  both passes: one CTA per hash-grid cell, its 27-cell neighbourhood staged in shared memory by TMA bulk copies, exact
+ *      per-particle lists of uint16 tile offsets (k_deform_t + k_deform_fin, k_force_t)
+ *   2  deformation pass as in 1, force pass as in 0 (the measured best on B200: the force pass gathers 80 B per pair and is
+ *      bound by shared-memory bandwidth in mode 1, by L1 in mode 0 where a record serves both particles of a cluster)
+ * Modes 1 and 2 return MIS_E_UNSUPPORTED if a neighbourhood of the scene holds more particles than the largest tile (the sim
+ * then stays in mode 0).  Default: the environment variable MIS_GATHER (0 / 1 / 2) if set, else 2 when the scene fits.      */
+int mis_set_gather_mode(MisSim* sim, int mode, void* stream);
+/* out[0] mode in effect, [1] active cells, [2] largest tile (particles), [3] largest cell, [4] / [5] tile capacity of the
+ * deform / force instantiation, [6] list blocks, [7] entries per block                                                       */
+int mis_get_gather_info(MisSim* sim, int out[8]);
 /* number of kernels this sim has launched so far (bench.py's gpu_launches)           */
 long long mis_launch_count(MisSim* sim);
 /* Measurement aid: n_steps steps with a CUDA event pair around every kernel launch on

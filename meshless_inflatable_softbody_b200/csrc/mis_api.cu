@@ -5,6 +5,7 @@
 #include "mis_neighbors.cuh"
 #include "mis_sort.cuh"
 #include "mis_cluster.cuh"
+#include "mis_tile.cuh"
 #include "mis_sdf_host.cuh"
 
 #include <math.h>
@@ -37,7 +38,8 @@ struct MisSim {
     bool pair_cells = true;           // MIS_PAIR_CELLS=0: keep the plain in-cell Morton order (A/B measurement)
     // caller-order copies
     float* x0_orig = nullptr;
-    int* coords = nullptr;
+    int* coords = nullptr;            // Warp's truncated cell coordinates (exported)
+    int* bcoords = nullptr;           // floor() coordinates: what the cell table and the Morton keys are built from
     int* cell_index = nullptr;
     // sort
     uint32_t* keys = nullptr;
@@ -67,6 +69,18 @@ struct MisSim {
     uint32_t* cl = nullptr;
     long long cl_cap = 0, cl_total = 0;
     float d2_limit = 0.f;
+    // shared-memory cell tiles (mis_tile.cuh): gather mode 1
+    struct Tile {
+        bool want_d = false, want_f = false, ok = false;      // tiles for the deformation pass / the force pass
+        uint32_t *wkey = nullptr, *order = nullptr;
+        int n_active = 0, max_tile = 0, max_own = 0, cap_d = 0, cap_f = 0;
+        int* tab = nullptr; long long tab_cap = 0;
+        uint32_t* flag = nullptr; unsigned long long* pos = nullptr;
+        uint32_t* nblocks = nullptr; unsigned long long* blk_start = nullptr; uint32_t* t_off = nullptr;
+        unsigned short* lists = nullptr; long long lists_cap = 0, total_blocks = 0;
+        float4* AB = nullptr;
+        int* max_dev = nullptr;
+    } tile;
     // cell-sorted state
     float4 *x0m = nullptr, *xv[2] = {nullptr, nullptr}, *vel = nullptr, *f1 = nullptr, *fel = nullptr;
     float4 *fext = nullptr, *freem = nullptr, *matl = nullptr, *RS = nullptr, *Fd = nullptr, *Ks = nullptr;
@@ -75,6 +89,7 @@ struct MisSim {
     double* loss_partial = nullptr;   // block partial sums of mis_accumulate_loss
     float* stage = nullptr;           // n*6 device staging for host-buffer variants
     int cur = 0;
+    cudaError_t enqueue_err = cudaSuccess;    // first error of a launch inside an enqueue_* helper (reported by the calling entry point)
     bool built = false, mass_set = false, material_set = false, started = false, dirty = true;
     bool forces_only = false;         // dirty because of fext / free_points alone: the stored elastic force is still valid
     long long launches = 0;
@@ -88,7 +103,8 @@ struct MisSim {
     float3 sdf_lo{}, sdf_hi{};
     float sdf_eps = 1e-3f;
     int *con_idx = nullptr, *con_idx2 = nullptr;
-    int* con_count = nullptr;                 // [0] broad-phase candidates, [1] particles in the contact band
+    int* con_count = nullptr;                 // [0] broad-phase candidates, [1] particles in the contact band, [2] FD rows, [3] overflow flag
+    int con_cap = 0;                          // rows one pass of the chain can take (MIS_CONTACT_ROWS, default 32768, at most n)
     float *con_pts = nullptr, *con_pts2 = nullptr, *con_s0 = nullptr;
     float4* fcon = nullptr;
     // the contact chain only reads the positions of the new frame, like k_deform_c: it runs beside it on a forked,
@@ -159,6 +175,7 @@ static void make_consts(MisSim* s) {
     c.sigma = 1.f / (pi * p.h * p.h * p.h);
     c.grad_c1 = c.sigma / (p.h * p.h);
     c.grad_c2 = 0.75f * c.sigma / p.h;
+    c.sigma4 = 0.25f * c.sigma; c.grad_q1 = 3.f * c.sigma / p.h; c.grad_q2 = 0.75f * c.sigma / p.h;
     c.dt = p.dt; c.half_dt2 = 0.5f * p.dt * p.dt; c.damping = p.damping;
     c.k_col = p.k_col; c.col_range = p.col_range;
     c.stiff_a = p.stiff_a; c.stiff_b = p.stiff_b;
@@ -203,11 +220,16 @@ extern "C" int mis_create(int n, const float* x0_dev, const MisParams* params, v
     s->C = Cs;
     { const char* e = getenv("MIS_PAIR_CELLS"); if (e && e[0] == '0') s->pair_cells = false; }
     { const char* e = getenv("MIS_MERGE_LISTS"); if (e && e[0] == '1') s->merge_lists = true; }
+    {   // gather mode: 2 (default) = shared-memory tiles for the deformation pass, cluster kernel for the force pass
+        const char* e = getenv("MIS_GATHER");
+        const int m = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+        s->tile.want_d = m >= 1; s->tile.want_f = m == 1;
+    }
     make_consts(s);
     s->d2_limit = find_d2_limit(s->p.h);
     const size_t N = (size_t)n;
 #define ALLOC(ptr, cnt) do { cudaError_t e_ = dalloc(&(ptr), (cnt)); if (e_ != cudaSuccess) { int r_ = fail(MIS_E_CUDA, std::string("cudaMalloc " #ptr ": ") + cudaGetErrorString(e_)); mis_destroy(s); return r_; } } while (0)
-    ALLOC(s->x0_orig, 3 * N); ALLOC(s->coords, 3 * N); ALLOC(s->cell_index, N);
+    ALLOC(s->x0_orig, 3 * N); ALLOC(s->coords, 3 * N); ALLOC(s->bcoords, 3 * N); ALLOC(s->cell_index, N);
     ALLOC(s->keys, N); ALLOC(s->subkey, N); ALLOC(s->perm, N); ALLOC(s->inv_perm, N);
     s->rs.nblocks = nblk(n, RS_TILE);
     ALLOC(s->rs.keys_alt, N); ALLOC(s->rs.vals_alt, N);
@@ -264,11 +286,13 @@ extern "C" int mis_destroy(MisSim* s) {
         cudaStreamDestroy(s->copy_stream);
         if (s->up_stream) { cudaStreamSynchronize(s->up_stream); cudaStreamDestroy(s->up_stream); }
     }
-    void* ptrs[] = {s->loss_partial, s->push, s->halo_mem, s->con_idx, s->con_idx2, s->con_count, s->con_pts, s->con_pts2, s->con_s0, s->fcon, s->x0_orig, s->coords, s->cell_index, s->keys, s->subkey, s->Ks, s->perm, s->inv_perm, s->rs.keys_alt, s->rs.vals_alt,
+    void* ptrs[] = {s->loss_partial, s->push, s->halo_mem, s->con_idx, s->con_idx2, s->con_count, s->con_pts, s->con_pts2, s->con_s0, s->fcon, s->x0_orig, s->coords, s->bcoords, s->cell_index, s->keys, s->subkey, s->Ks, s->perm, s->inv_perm, s->rs.keys_alt, s->rs.vals_alt,
                     s->rs.hist, s->rs.hist_scanned, s->rs.tile_tmp, s->bounds_dev, s->max_k_dev, s->cell_start, s->cell_end,
                     s->cell_lin_sorted, s->nbr_count, s->nbr_start, s->scan_tmp, s->nbr, s->cl_count, s->cl_start, s->cl, s->x0m, s->xv[0], s->xv[1], s->vel,
                     s->f1, s->fel, s->fext, s->freem, s->matl, s->RS, s->Fd, s->Apq, s->scratch4, s->stage};
     for (void* p : ptrs) if (p) cudaFree(p);
+    void* tptrs[] = {s->tile.wkey, s->tile.order, s->tile.tab, s->tile.flag, s->tile.pos, s->tile.nblocks, s->tile.blk_start, s->tile.t_off, s->tile.lists, s->tile.AB, s->tile.max_dev};
+    for (void* p : tptrs) if (p) cudaFree(p);
     delete s;
     return MIS_OK;
 }
@@ -310,6 +334,87 @@ static int build_cluster_lists(MisSim* s, cudaStream_t st) {
     return MIS_OK;
 }
 
+// ---- shared-memory cell tiles: active-cell table, uint16 tile-offset lists (mis_tile.cuh).  Needs the exact lists.
+static const int TILE_CAPS_D[] = {2048, 2560, 3072, 4096};
+static const int TILE_CAPS_F[] = {2048, 2560, 2816};
+template <int CAP, int MINB> static cudaError_t tile_attr_d() {
+    return cudaFuncSetAttribute(k_deform_t<CAP, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_deform<CAP>());
+}
+template <int CAP> static cudaError_t tile_attr_f() {
+    return cudaFuncSetAttribute(k_force_t<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_force<CAP>());
+}
+static int build_tiles(MisSim* s, cudaStream_t st) {
+    MisSim::Tile& t = s->tile;
+    const int n = s->n;
+    t.ok = false;
+    if (!t.flag) {
+        CK(dalloc(&t.flag, (size_t)n)); CK(dalloc(&t.pos, (size_t)n + 1)); CK(dalloc(&t.nblocks, (size_t)n));
+        CK(dalloc(&t.blk_start, (size_t)n + 1)); CK(dalloc(&t.t_off, (size_t)n)); CK(dalloc(&t.AB, 5 * (size_t)n)); CK(dalloc(&t.max_dev, 2));
+        CK(dalloc(&t.wkey, (size_t)n)); CK(dalloc(&t.order, (size_t)n));
+    }
+    const int3 cdim = make_int3(s->cell_dim[0], s->cell_dim[1], s->cell_dim[2]);
+    k_tile_flag<<<nblk(n, 256), 256, 0, st>>>(s->cell_lin_sorted, s->cell_start, n, t.flag);
+    CK_LAUNCH(); s->launches++;
+    s->launches += exclusive_scan<unsigned long long>(t.flag, t.pos, n, s->scan_tmp, st);
+    unsigned long long na = 0;
+    CK(cudaMemcpyAsync(&na, t.pos + n, sizeof na, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemsetAsync(t.max_dev, 0, 2 * sizeof(int), st));
+    CK(cudaStreamSynchronize(st));
+    t.n_active = (int)na;
+    if ((long long)t.n_active > t.tab_cap) {
+        if (t.tab) cudaFree(t.tab);
+        t.tab = nullptr;
+        CK(dalloc(&t.tab, (size_t)t.n_active * TT_STRIDE));
+        t.tab_cap = t.n_active;
+    }
+    k_tile_tab<<<nblk((long long)n * 32, 256), 256, 0, st>>>(t.flag, t.pos, s->cell_lin_sorted, s->cell_start, s->cell_end, cdim, n, t.tab, t.max_dev,
+                                                            s->nbr_start, t.wkey, t.order);
+    CK_LAUNCH(); s->launches++;
+    s->launches += radix_sort_pairs(t.wkey, t.order, t.n_active, 20, s->rs, st);      // longest cell first
+    CK_LAUNCH();
+    k_tile_count<<<nblk(n, 256), 256, 0, st>>>(s->nbr_count, n, t.nblocks);
+    CK_LAUNCH(); s->launches++;
+    s->launches += exclusive_scan<unsigned long long>(t.nblocks, t.blk_start, n, s->scan_tmp, st);
+    int mx[2] = {0, 0};
+    unsigned long long tb = 0;
+    CK(cudaMemcpyAsync(mx, t.max_dev, sizeof mx, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&tb, t.blk_start + n, sizeof tb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    t.max_tile = mx[0]; t.max_own = mx[1]; t.total_blocks = (long long)tb;
+    t.cap_d = t.cap_f = 0;
+    for (int c : TILE_CAPS_D) if (!t.cap_d && t.max_tile <= c) t.cap_d = c;
+    for (int c : TILE_CAPS_F) if (!t.cap_f && t.max_tile <= c) t.cap_f = c;
+    if (!t.cap_d || !t.cap_f) return MIS_OK;          // a neighbourhood too dense for one tile: the cluster kernels run instead
+    if (t.total_blocks > t.lists_cap || !t.lists) {
+        if (t.lists) cudaFree(t.lists);
+        t.lists = nullptr;
+        CK(dalloc(&t.lists, (size_t)(t.total_blocks + 1) * TILE_BLOCK));
+        t.lists_cap = t.total_blocks;
+    }
+    k_tile_lists<<<nblk((long long)n * 32, 256), 256, 0, st>>>(s->nbr_start, s->nbr, s->nbr_count, s->cell_lin_sorted, s->cell_start, t.pos, t.tab, cdim, n,
+                                                              t.blk_start, t.t_off, t.lists);
+    CK_LAUNCH(); s->launches++;
+    // per device: the opt-in shared-memory size of the instantiations this scene uses
+    cudaError_t e = cudaSuccess;
+    switch (t.cap_d) {
+        case 2048: e = tile_attr_d<2048, 3>(); break; case 2560: e = tile_attr_d<2560, 2>(); break;
+        case 3072: e = tile_attr_d<3072, 2>(); break; default: e = tile_attr_d<4096, 1>(); break;
+    }
+    CK(e);
+    switch (t.cap_f) { case 2048: e = tile_attr_f<2048>(); break; case 2560: e = tile_attr_f<2560>(); break; default: e = tile_attr_f<2816>(); break; }
+    CK(e);
+    t.ok = true;
+    return MIS_OK;
+}
+static TileView make_tile_view(MisSim* s) {
+    TileView t;
+    t.order = s->tile.order; t.tab = s->tile.tab; t.n_active = s->tile.n_active; t.lists = (const uint4*)s->tile.lists;
+    t.t_off = s->tile.t_off; t.t_cnt = s->nbr_count; t.AB = s->tile.AB;
+    return t;
+}
+static bool use_tiles_d(const MisSim* s) { return s->tile.want_d && s->tile.ok && !s->p.two_pass_deform; }
+static bool use_tiles_f(const MisSim* s) { return s->tile.want_f && s->tile.ok && !s->p.symmetric_pair; }
+
 extern "C" int mis_build_neighbors(MisSim* s, void* stream) {
     if (!s) return fail(MIS_E_INVALID, "null sim");
     cudaStream_t st = (cudaStream_t)stream;
@@ -319,7 +424,7 @@ extern "C" int mis_build_neighbors(MisSim* s, void* stream) {
     int hb[6] = {INT_MAX, INT_MAX, INT_MAX, INT_MIN, INT_MIN, INT_MIN};
     CK(cudaMemcpyAsync(s->bounds_dev, hb, sizeof hb, cudaMemcpyHostToDevice, st));
     k_cell_coords<<<nblk(n, 256), 256, 0, st>>>(s->x0_orig, n, inv_cw, s->p.grid_x, s->p.grid_y, s->p.grid_z,
-                                                s->coords, s->cell_index, s->subkey, s->bounds_dev);
+                                                s->coords, s->bcoords, s->cell_index, s->subkey, s->bounds_dev);
     CK_LAUNCH(); s->launches++;
     CK(cudaMemcpyAsync(hb, s->bounds_dev, sizeof hb, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -349,11 +454,11 @@ extern "C" int mis_build_neighbors(MisSim* s, void* stream) {
     while ((1 << bits) < maxdim) bits++;
     // in-cell Morton refinement: as many of its 9 bits as fit a 32-bit key (multiples of 3)
     s->sub_bits = 3 * bits + 9 <= 32 ? 9 : (3 * bits + 6 <= 32 ? 6 : (3 * bits + 3 <= 32 ? 3 : 0));
-    k_cell_keys<<<nblk(n, 256), 256, 0, st>>>(s->coords, s->subkey, n, cmin, s->sub_bits, s->keys);
+    k_cell_keys<<<nblk(n, 256), 256, 0, st>>>(s->bcoords, s->subkey, n, cmin, s->sub_bits, s->keys);
     CK_LAUNCH(); s->launches++;
     s->launches += radix_sort_pairs(s->keys, s->perm, n, 3 * bits + s->sub_bits, s->rs, st);
     CK_LAUNCH();
-    k_cell_table<<<nblk(n, 256), 256, 0, st>>>(s->keys, s->perm, s->coords, s->x0_orig, n, cmin, cdim, s->sub_bits,
+    k_cell_table<<<nblk(n, 256), 256, 0, st>>>(s->keys, s->perm, s->bcoords, s->x0_orig, n, cmin, cdim, s->sub_bits,
                                                s->cell_start, s->cell_end, s->cell_lin_sorted, s->inv_perm, s->x0m);
     CK_LAUNCH(); s->launches++;
     if (s->C > 1 && s->pair_cells) {
@@ -387,6 +492,7 @@ extern "C" int mis_build_neighbors(MisSim* s, void* stream) {
     if (rc) return rc;
     drop_graph(s);                            // a captured chunk holds the old list pointers
     s->built = true;
+    if (s->tile.want_d || s->tile.want_f) { rc = build_tiles(s, st); if (rc) return rc; }
     return MIS_OK;
 }
 
@@ -510,8 +616,16 @@ extern "C" int mis_set_dirichlet(MisSim* s, const float* free_dev, void* stream)
 static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e && e[0] ? atoi(e) : dflt; }
 template <int C, int G> static void launch_deform(MisSim* s, const View& v, cudaStream_t st) {
     const int nc = (s->n + C - 1) / C;
-    static int carve = -2;                    // tuning hook: MIS_DEFORM_CARVEOUT = preferred shared-memory carve-out in percent
-    if (carve == -2) { carve = env_int("MIS_DEFORM_CARVEOUT", -1); if (carve >= 0) cudaFuncSetAttribute(k_deform_c<C, G, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve); }
+    static int carve_dev[64];                 // tuning hook: MIS_DEFORM_CARVEOUT = preferred shared-memory carve-out in percent (a per-device attribute)
+    static bool carve_init[64] = {};
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    dev_ &= 63;
+    if (!carve_init[dev_]) {
+        carve_init[dev_] = true;
+        carve_dev[dev_] = env_int("MIS_DEFORM_CARVEOUT", -1);
+        if (carve_dev[dev_] >= 0) cudaFuncSetAttribute(k_deform_c<C, G, false>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_dev[dev_]);
+    }
     k_deform_c<C, G, false><<<nblk((long long)nc * G, STEP_THREADS), STEP_THREADS, 0, st>>>(v, s->c);
 }
 template <int C> static void launch_deform2(MisSim* s, const View& v, cudaStream_t st) {
@@ -537,7 +651,30 @@ template <int C> static void launch_force_sym(MisSim* s, const View& v, int mode
             default: FN<4, 32>(__VA_ARGS__); break;                                               \
         }                                                                                         \
     } while (0)
+static void enqueue_deform_tile(MisSim* s, const View& v, cudaStream_t st) {
+    const TileView t = make_tile_view(s);
+    const int g = s->tile.n_active;
+    switch (s->tile.cap_d) {
+        case 2048: k_deform_t<2048, 3><<<g, TILE_THREADS_D, tile_smem_deform<2048>(), st>>>(v, s->c, t); break;
+        case 2560: k_deform_t<2560, 2><<<g, TILE_THREADS_D, tile_smem_deform<2560>(), st>>>(v, s->c, t); break;
+        case 3072: k_deform_t<3072, 2><<<g, TILE_THREADS_D, tile_smem_deform<3072>(), st>>>(v, s->c, t); break;
+        default:   k_deform_t<4096, 1><<<g, TILE_THREADS_D, tile_smem_deform<4096>(), st>>>(v, s->c, t); break;
+    }
+    k_deform_fin<<<nblk(s->n, 128), 128, 0, st>>>(v, s->c, s->tile.AB);
+    s->launches += 2;
+}
+static void enqueue_force_tile(MisSim* s, const View& v, int mode, cudaStream_t st) {
+    const TileView t = make_tile_view(s);
+    const int g = s->tile.n_active;
+    switch (s->tile.cap_f) {
+        case 2048: k_force_t<2048><<<g, TILE_THREADS_F, tile_smem_force<2048>(), st>>>(v, s->c, t, mode); break;
+        case 2560: k_force_t<2560><<<g, TILE_THREADS_F, tile_smem_force<2560>(), st>>>(v, s->c, t, mode); break;
+        default:   k_force_t<2816><<<g, TILE_THREADS_F, tile_smem_force<2816>(), st>>>(v, s->c, t, mode); break;
+    }
+    s->launches++;
+}
 static void enqueue_deform(MisSim* s, const View& v, cudaStream_t st) {
+    if (use_tiles_d(s)) { enqueue_deform_tile(s, v, st); return; }
     if (s->p.two_pass_deform) {       // reference two-loop order: accuracy studies, fixed 8 lanes per cluster
         if (s->C == 1) launch_deform2<1>(s, v, st); else if (s->C == 2) launch_deform2<2>(s, v, st); else launch_deform2<4>(s, v, st);
     } else {
@@ -546,6 +683,7 @@ static void enqueue_deform(MisSim* s, const View& v, cudaStream_t st) {
     s->launches++;
 }
 static void enqueue_force(MisSim* s, const View& v, int mode, cudaStream_t st) {
+    if (use_tiles_f(s)) { enqueue_force_tile(s, v, mode, st); return; }
     if (s->p.symmetric_pair) {        // sim_taichi.py pair force, fixed 8 lanes per cluster
         if (s->C == 1) launch_force_sym<1>(s, v, mode, st); else if (s->C == 2) launch_force_sym<2>(s, v, mode, st); else launch_force_sym<4>(s, v, mode, st);
     } else {
@@ -572,42 +710,50 @@ static void enqueue_halo_sync(MisSim* s, cudaStream_t st) {
 // obstacle contact at the now-current positions: broad phase (bounding box) -> MLP values -> narrow phase (contact band)
 // -> three forward-difference evaluations of the particles in contact -> penalty force.  No host synchronisation:
 // the live row counts stay on the device and dead row-blocks of the GEMM grid exit at once.
-static void enqueue_contact(MisSim* s, const View& v, cudaStream_t st) {
-    if (!s->sdf) return;
-    const int n = s->n;
+static cudaError_t enqueue_contact(MisSim* s, const View& v, cudaStream_t st) {
+    if (!s->sdf) return cudaSuccess;
+    const int n = s->n, cap = s->con_cap;
     MisSdf* net = s->sdf;
-    cudaMemsetAsync(s->con_count, 0, 3 * sizeof(int), st);
-    k_contact_select<<<nblk(n, 256), 256, 0, st>>>(v.xcur, n, s->sdf_xf, s->sdf_lo, s->sdf_hi, s->con_idx, s->con_count, s->con_pts, s->fcon);
+    cudaError_t e = cudaMemsetAsync(s->con_count, 0, 3 * sizeof(int), st);        // [3] (overflow) is sticky until read
+    if (e != cudaSuccess) return e;
+    k_contact_select<<<nblk(n, 256), 256, 0, st>>>(v.xcur, n, s->sdf_xf, s->sdf_lo, s->sdf_hi, cap, s->con_idx, s->con_count, s->con_pts, s->fcon);
     const long long l0 = net->launches;
     int fb = 0;
     const int H = net->H;
-    sdf_forward(net, s->con_pts, nullptr, n, s->con_count, s->sdf_xf, make_float3(0.f, 0.f, 0.f), nullptr, st, 0, &fb);
-    launch_k(k_contact_last_narrow, dim3(148 * 2), dim3(256), 0, st, true,
-             (const float*)net->act[fb][0], (const float*)net->act[fb][1], n, (const int*)s->con_count, (const float*)net->wl, (const float*)net->bl, H, s->p.col_range,
-             (const int*)s->con_idx, (const float*)s->con_pts, s->con_idx2, s->con_pts2, s->con_s0, s->con_count + 1);
-    // the three forward differences of the in-contact particles as ONE pass of 3 x count rows (row 3 r + axis);
-    // the chain's capacity is n rows, so at most n / 3 particles can be in the band at once (far more than a surface holds)
-    const float e = s->sdf_eps;
-    sdf_forward(net, s->con_pts2, nullptr, n, s->con_count + 2, s->sdf_xf, make_float3(e, 0.f, 0.f), nullptr, st, 1, &fb, true);
-    launch_k(k_contact_last_apply, dim3(148 * 2), dim3(256), 0, st, true,
-             (const float*)net->act[fb][0], (const float*)net->act[fb][1], n, (const int*)(s->con_count + 1), (const float*)net->wl, (const float*)net->bl, H,
-             (const float*)s->con_s0, (const int*)s->con_idx2, 1.f / e, s->sdf_xf, s->p.col_range, s->p.k_col, s->fcon);
+    e = sdf_forward(net, s->con_pts, nullptr, cap, s->con_count, s->sdf_xf, make_float3(0.f, 0.f, 0.f), nullptr, st, 0, &fb);
+    if (e != cudaSuccess) return e;
+    e = launch_k(k_contact_last_narrow, dim3(148 * 2), dim3(256), 0, st, true,
+                 (const float*)net->act[fb][0], (const float*)net->act[fb][1], cap, (const int*)s->con_count, (const float*)net->wl, (const float*)net->bl, H, s->p.col_range,
+                 (const int*)s->con_idx, (const float*)s->con_pts, s->con_idx2, s->con_pts2, s->con_s0, s->con_count + 1);
+    if (e != cudaSuccess) return e;
+    // the three forward differences of the in-contact particles as ONE pass of 3 x count rows (row 3 r + axis): at most cap / 3
+    // particles in the band at once; beyond that the narrow phase raises the overflow flag
+    const float ep = s->sdf_eps;
+    e = sdf_forward(net, s->con_pts2, nullptr, cap, s->con_count + 2, s->sdf_xf, make_float3(ep, 0.f, 0.f), nullptr, st, 1, &fb, true);
+    if (e != cudaSuccess) return e;
+    e = launch_k(k_contact_last_apply, dim3(148 * 2), dim3(256), 0, st, true,
+                 (const float*)net->act[fb][0], (const float*)net->act[fb][1], cap, (const int*)(s->con_count + 1), (const float*)net->wl, (const float*)net->bl, H,
+                 (const float*)s->con_s0, (const int*)s->con_idx2, 1.f / ep, s->sdf_xf, s->p.col_range, s->p.k_col, s->fcon);
+    if (e != cudaSuccess) return e;
     s->launches += 3 + (net->launches - l0);
+    return cudaGetLastError();
 }
 
 // k_deform_c and the contact chain of one frame: both depend on the new positions only
 static void enqueue_deform_contact(MisSim* s, const View& v, cudaStream_t st) {
+    cudaError_t e;
     if (s->sdf && s->side_stream && !s->serial_contact) {
         cudaEventRecord(s->ev_fork, st);
         cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0);
-        enqueue_contact(s, v, s->side_stream);
+        e = enqueue_contact(s, v, s->side_stream);
         cudaEventRecord(s->ev_join, s->side_stream);
         enqueue_deform(s, v, st);
         cudaStreamWaitEvent(st, s->ev_join, 0);
     } else {
         enqueue_deform(s, v, st);
-        enqueue_contact(s, v, st);
+        e = enqueue_contact(s, v, st);
     }
+    if (e != cudaSuccess && s->enqueue_err == cudaSuccess) s->enqueue_err = e;      // surfaced by mis_step / prime
 }
 
 // frame-0 style priming at the current x: elastic force, force_1 and the next position
@@ -625,6 +771,7 @@ static int prime(MisSim* s, cudaStream_t st) {
             enqueue_force(s, v, MODE_PRIME, st);
         }
         enqueue_halo_sync(s, st);
+        if (s->enqueue_err != cudaSuccess) { cudaError_t e = s->enqueue_err; s->enqueue_err = cudaSuccess; CK(e); }
         CK_LAUNCH();
     }
     s->dirty = false; s->forces_only = false;
@@ -711,6 +858,7 @@ extern "C" int mis_step(MisSim* s, int n_steps, void* stream) {
         for (; done < n_steps; done++) { int rc = launch_step_graph(s, 1, st); if (rc) return rc; }
     }
     for (; done < n_steps; done++) enqueue_one_step(s, st);
+    if (s->enqueue_err != cudaSuccess) { cudaError_t e = s->enqueue_err; s->enqueue_err = cudaSuccess; CK(e); }
     CK_LAUNCH();
     return MIS_OK;
 }
@@ -972,6 +1120,26 @@ extern "C" int mis_accumulate_loss(MisSim* s, const float* target_x_dev, const f
     return MIS_OK;
 }
 
+extern "C" int mis_set_gather_mode(MisSim* s, int mode, void* stream) {
+    if (!s || mode < 0 || mode > 2) return fail(MIS_E_INVALID, "mis_set_gather_mode: mode must be 0, 1 or 2");
+    drop_graph(s);
+    s->tile.want_d = mode >= 1; s->tile.want_f = mode == 1;
+    s->dirty = true; s->forces_only = false;
+    if (mode && s->built && !s->tile.ok) { int rc = build_tiles(s, (cudaStream_t)stream); if (rc) return rc; }
+    if (mode && !s->tile.ok) {
+        s->tile.want_d = s->tile.want_f = false;
+        return fail(MIS_E_UNSUPPORTED, "a 27-cell neighbourhood of this scene exceeds the largest shared-memory tile");
+    }
+    return MIS_OK;
+}
+
+extern "C" int mis_get_gather_info(MisSim* s, int out[8]) {
+    if (!s || !out) return fail(MIS_E_INVALID, "null argument");
+    out[0] = use_tiles_d(s) ? (use_tiles_f(s) ? 1 : 2) : 0; out[1] = s->tile.n_active; out[2] = s->tile.max_tile; out[3] = s->tile.max_own;
+    out[4] = s->tile.cap_d; out[5] = s->tile.cap_f; out[6] = (int)(s->tile.total_blocks >> 31 ? 0x7fffffff : s->tile.total_blocks); out[7] = TILE_BLOCK;
+    return MIS_OK;
+}
+
 extern "C" long long mis_launch_count(MisSim* s) { return s ? s->launches : 0; }
 
 // n_steps steps launched one kernel at a time with a CUDA event pair around each launch on
@@ -979,6 +1147,7 @@ extern "C" long long mis_launch_count(MisSim* s) { return s ? s->launches : 0; }
 extern "C" int mis_profile_step(MisSim* s, int n_steps, void* stream, double* ms_deform, double* ms_force) {
     if (!s || n_steps <= 0) return fail(MIS_E_INVALID, "bad argument");
     if (!s->started) return fail(MIS_E_STATE, "mis_profile_step before mis_startup / mis_set_state");
+    if (s->sdf) return fail(MIS_E_UNSUPPORTED, "mis_profile_step times the two gather kernels alone: remove the obstacle first (mis_set_sdf_contact(sim, NULL, ...))");
     cudaStream_t st = (cudaStream_t)stream;
     if (s->dirty) { int rc = prime(s, st); if (rc) return rc; }
     std::vector<cudaEvent_t> ev(3 * (size_t)n_steps);
@@ -1164,7 +1333,14 @@ extern "C" int mis_set_sdf_contact(MisSim* s, MisSdf* sdf, const float* xform_ho
         s->serial_contact = e && e[0] == '1';
     }
     CK(cudaMemsetAsync(s->con_count, 0, 4 * sizeof(int), (cudaStream_t)stream));
-    CK(sdf_reserve(sdf, s->n));
+    {   // rows one pass of the chain can take: the activations are 16 KB per row (4 buffers x H floats), so the capacity is bounded
+        // (not n: 10 M particles would ask for 164 GB); an over-full bounding box or contact band raises the overflow flag
+        const int want = env_int("MIS_CONTACT_ROWS", 32768);
+        int cap = want < 384 ? 384 : want;
+        if (cap > s->n) cap = s->n;
+        s->con_cap = (cap + 127) / 128 * 128;
+    }
+    CK(sdf_reserve(sdf, s->con_cap));
     CK(cudaFuncSetAttribute(k_sdf_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES));
     s->sdf = sdf; s->sdf_xf = make_xform(xform_host); s->sdf_eps = fd_eps;
     s->sdf_lo = make_float3(bbox_host[0], bbox_host[1], bbox_host[2]);
@@ -1186,7 +1362,14 @@ extern "C" int mis_get_contact_count(MisSim* s, void* stream, int* count) {
     if (!s || !count) return fail(MIS_E_INVALID, "null argument");
     count[0] = count[1] = 0;
     if (!s->sdf) return MIS_OK;
-    CK(cudaMemcpyAsync(count, s->con_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    int host[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(host, s->con_count, 4 * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CK(cudaStreamSynchronize((cudaStream_t)stream));
+    count[0] = host[0]; count[1] = host[1];
+    if (host[3]) {
+        CK(cudaMemsetAsync(s->con_count + 3, 0, sizeof(int), (cudaStream_t)stream));
+        return fail(MIS_E_UNSUPPORTED, "obstacle contact overflow: more particles in the obstacle's bounding box (or 3 x contact band) than the "
+                                       "chain's row capacity (MIS_CONTACT_ROWS, " + std::to_string(s->con_cap) + "); their contact force was dropped");
+    }
     return MIS_OK;
 }

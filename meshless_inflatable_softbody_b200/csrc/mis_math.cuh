@@ -15,6 +15,9 @@ struct Consts {
     float sigma;        // 1 / (pi h^3)
     float grad_c1;      // sigma / h^2
     float grad_c2;      // 0.75 * sigma / h      (1<=q<2 branch: -c2 (2-q)^2 / r)
+    float sigma4;       // sigma / 4
+    float grad_q1;      // 3 sigma / h           beta = (grad_q1 t1^2 - grad_q2 t2^2) / r
+    float grad_q2;      // 0.75 sigma / h
     float dt, half_dt2, damping;
     float k_col, col_range;
     float stiff_a, stiff_b;
@@ -31,13 +34,16 @@ __device__ __forceinline__ float3 xyz(float4 a) { return make_float3(a.x, a.y, a
 // W(|xij|) for a listed neighbour (q < 2 by construction of the list), sim.py:133-141.
 // r2 = |xij|^2.  rsqrt-based: value parity is to fp32 round-off, membership of the
 // neighbour set is decided exactly elsewhere (mis_neighbors.cuh).
+// Branch-free form used by all three helpers: with t2 = max(2 - q, 0), t1 = max(1 - q, 0) the piecewise cubic of sim.py:137-141
+// is the cubic B-spline identity
+//     W = sigma (t2^3 / 4 - t1^3),        dW/dq = sigma (3 t1^2 - 3/4 t2^2),        nabla_W = (dW/dq) / (r h) * xij
+// (q < 1: 1/4 (2-q)^3 - (1-q)^3 = 1 - 1.5 q^2 + 0.75 q^3; 1 <= q < 2: the first term alone; q >= 2: zero), so no lane diverges on
+// the branch of the kernel and the compiler needs neither selects nor a reconvergence point inside the pair loop.
 __device__ __forceinline__ float kernel_W(float r2, const Consts& c) {
     float rinv = rsqrtf(fmaxf(r2, 1e-30f));
     float q = r2 * rinv * c.inv_h;
-    float t = fmaxf(2.f - q, 0.f);
-    float w_out = 0.25f * t * t * t;
-    float w_in = 1.f - 1.5f * q * q + 0.75f * q * q * q;
-    return c.sigma * (q < 1.f ? w_in : w_out);
+    float t2 = fmaxf(2.f - q, 0.f), t1 = fmaxf(1.f - q, 0.f);
+    return c.sigma * (0.25f * t2 * t2 * t2 - t1 * t1 * t1);
 }
 
 // nabla_W(xij) = beta(|xij|) * xij, sim.py:143-151.  Returns beta.
@@ -54,20 +60,22 @@ __device__ __forceinline__ float rsqrt_normal(float x) {
 __device__ __forceinline__ float kernel_gradW_coef(float r2, const Consts& c) {
     float rinv = rsqrt_normal(fmaxf(r2, 1e-30f));
     float q = r2 * rinv * c.inv_h;
-    float t = fmaxf(2.f - q, 0.f);
-    float b_out = -c.grad_c2 * t * t * rinv;
-    float b_in = c.grad_c1 * (-3.f + 2.25f * q);
-    return q < 1.f ? b_in : b_out;
+    float t2 = fmaxf(2.f - q, 0.f), t1 = fmaxf(1.f - q, 0.f);
+    float e = c.grad_q1 * (t1 * t1);
+    e = fmaf(-c.grad_q2, t2 * t2, e);                 // sigma / h (3 t1^2 - 3/4 t2^2)
+    return e * rinv;
 }
 
 // Both at once (pass A needs W, pass F needs beta; the fused kernel wants both).
 __device__ __forceinline__ void kernel_W_and_coef(float r2, const Consts& c, float& w, float& beta) {
     float rinv = rsqrt_normal(fmaxf(r2, 1e-30f));
     float q = r2 * rinv * c.inv_h;
-    float t = fmaxf(2.f - q, 0.f);
-    bool in = q < 1.f;
-    w = c.sigma * (in ? (1.f - 1.5f * q * q + 0.75f * q * q * q) : 0.25f * t * t * t);
-    beta = in ? c.grad_c1 * (-3.f + 2.25f * q) : -c.grad_c2 * t * t * rinv;
+    float t2 = fmaxf(2.f - q, 0.f), t1 = fmaxf(1.f - q, 0.f);
+    float t2s = t2 * t2, t1s = t1 * t1;
+    w = (c.sigma4 * t2s) * t2 - (c.sigma * t1s) * t1;
+    float e = c.grad_q1 * t1s;
+    e = fmaf(-c.grad_q2, t2s, e);
+    beta = e * rinv;
 }
 
 // ---------------------------------------------------------------- rotation

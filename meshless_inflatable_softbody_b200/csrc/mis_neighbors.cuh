@@ -30,29 +30,31 @@ __device__ __forceinline__ uint32_t morton3(uint32_t x, uint32_t y, uint32_t z) 
     return part1by2(x) | (part1by2(y) << 1) | (part1by2(z) << 2);
 }
 
-// per particle (caller order): integer cell coords, wp.HashGrid linear cell index, bounds
+// per particle (caller order): Warp's integer cell coords and linear cell index (exported, bit-exact), and the coordinates the
+// internal binning uses.  Warp truncates toward zero (int(p / cw)), which makes every cell that touches a coordinate plane twice
+// as wide (x in (-cw, cw) is ONE cell): up to 8x the particles in a cell at the origin.  Any binning with cells >= the support
+// radius gives the same neighbour sets, so the internal structure bins with floor(): uniform cells, balanced tiles.
 __global__ void __launch_bounds__(256) k_cell_coords(const float* __restrict__ x0, int n, float inv_cw,
                                                      int gx, int gy, int gz,
-                                                     int* __restrict__ coords, int* __restrict__ cell_index,
+                                                     int* __restrict__ coords, int* __restrict__ bcoords, int* __restrict__ cell_index,
                                                      uint32_t* __restrict__ subkey,
-                                                     int* __restrict__ bounds /* min xyz, max xyz */) {
+                                                     int* __restrict__ bounds /* min xyz, max xyz of the binning coords */) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int cx = INT_MAX, cy = INT_MAX, cz = INT_MAX, mx = INT_MIN, my = INT_MIN, mz = INT_MIN;
     if (i < n) {
-        cx = mx = cell_coord(x0[3 * i + 0], inv_cw);
-        cy = my = cell_coord(x0[3 * i + 1], inv_cw);
-        cz = mz = cell_coord(x0[3 * i + 2], inv_cw);
-        coords[3 * i + 0] = cx; coords[3 * i + 1] = cy; coords[3 * i + 2] = cz;
-        // position inside the cell in eighths of the span (-1, 1) around the truncated coordinate: orders the
-        // particles of a cell along a fine Morton curve (locality of the neighbour runs; no effect on results)
-        float fx = __fmul_rn(x0[3 * i + 0], inv_cw) - (float)cx, fy = __fmul_rn(x0[3 * i + 1], inv_cw) - (float)cy,
-              fz = __fmul_rn(x0[3 * i + 2], inv_cw) - (float)cz;
-        int sx = min(max((int)floorf((fx + 1.f) * 4.f), 0), 7), sy = min(max((int)floorf((fy + 1.f) * 4.f), 0), 7),
-            sz = min(max((int)floorf((fz + 1.f) * 4.f), 0), 7);
+        const float sx_ = __fmul_rn(x0[3 * i + 0], inv_cw), sy_ = __fmul_rn(x0[3 * i + 1], inv_cw), sz_ = __fmul_rn(x0[3 * i + 2], inv_cw);
+        const int tx = __float2int_rz(sx_), ty = __float2int_rz(sy_), tz = __float2int_rz(sz_);      // Warp: truncation
+        coords[3 * i + 0] = tx; coords[3 * i + 1] = ty; coords[3 * i + 2] = tz;
+        cx = mx = __float2int_rd(sx_); cy = my = __float2int_rd(sy_); cz = mz = __float2int_rd(sz_);  // binning: floor
+        bcoords[3 * i + 0] = cx; bcoords[3 * i + 1] = cy; bcoords[3 * i + 2] = cz;
+        // position inside the cell in eighths: orders the particles of a cell along a fine Morton curve (locality of the
+        // neighbour runs; no effect on results)
+        float fx = sx_ - (float)cx, fy = sy_ - (float)cy, fz = sz_ - (float)cz;
+        int sx = min(max((int)(fx * 8.f), 0), 7), sy = min(max((int)(fy * 8.f), 0), 7), sz = min(max((int)(fz * 8.f), 0), 7);
         subkey[i] = morton3((uint32_t)sx, (uint32_t)sy, (uint32_t)sz);
         // hash_grid_index: +2^20 origin, clamp at 0, mod dim, x fastest
         const int origin = 1 << 20;
-        int hx = max(cx + origin, 0) % gx, hy = max(cy + origin, 0) % gy, hz = max(cz + origin, 0) % gz;
+        int hx = max(tx + origin, 0) % gx, hy = max(ty + origin, 0) % gy, hz = max(tz + origin, 0) % gz;
         cell_index[i] = hz * (gx * gy) + hy * gx + hx;
     }
     // warp-reduce the bounds, one atomic per warp

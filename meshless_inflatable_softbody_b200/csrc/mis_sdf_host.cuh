@@ -98,7 +98,10 @@ inline cudaError_t sdf_reserve(MisSdf* s, int rows) {
 // pdl_first: layer 0 is a programmatic dependent launch of the caller's previous kernel (which must call pdl_trigger / exit).
 inline cudaError_t sdf_forward(MisSdf* s, const float* pts, const int* idx, int rows, const int* m_count, const SdfXform& xf, float3 shift,
                                float* out, cudaStream_t st, int fd3 = 0, int* final_buf = nullptr, bool pdl_first = false) {
-    static bool attr_set = false;
+    static bool attr_set_dev[64] = {};                 // the opt-in shared-memory size is a per-DEVICE function attribute
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    bool& attr_set = attr_set_dev[dev_ & 63];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_sdf_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, SDF_SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sdf_gemm_sk, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM_BYTES);
@@ -178,7 +181,8 @@ __global__ void __launch_bounds__(256) k_sdf_fd_grad(const float* __restrict__ v
 
 // ---------------------------------------------------------------- per-step contact (extension of sim.py:238-244)
 // broad phase: cell-sorted particles whose model-space position lies in the obstacle's bounding box (+ margin)
-__global__ void __launch_bounds__(256) k_contact_select(const float4* __restrict__ xcur, int n, SdfXform xf, float3 lo, float3 hi,
+// count[0] = candidates appended (capped at `cap` rows; count[3] is raised when the box holds more than the chain can evaluate)
+__global__ void __launch_bounds__(256) k_contact_select(const float4* __restrict__ xcur, int n, SdfXform xf, float3 lo, float3 hi, int cap,
                                                         int* __restrict__ idx, int* __restrict__ count, float* __restrict__ pts_out,
                                                         float4* __restrict__ fcon) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -202,8 +206,12 @@ __global__ void __launch_bounds__(256) k_contact_select(const float4* __restrict
     basep = __shfl_sync(0xffffffffu, basep, __ffs(m) - 1);
     if (in) {
         const int r = basep + __popc(m & ((1u << lane) - 1));
-        idx[r] = s;
-        pts_out[3 * (size_t)r] = p.x; pts_out[3 * (size_t)r + 1] = p.y; pts_out[3 * (size_t)r + 2] = p.z;
+        if (r < cap) {
+            idx[r] = s;
+            pts_out[3 * (size_t)r] = p.x; pts_out[3 * (size_t)r + 1] = p.y; pts_out[3 * (size_t)r + 2] = p.z;
+        } else {
+            count[3] = 1;                                 // overflow: reported by mis_get_contact_count, never silent
+        }
     }
 }
 
@@ -222,6 +230,7 @@ __global__ void __launch_bounds__(256) k_contact_last_narrow(const float* __rest
         const float v = sdf_last_row(Xhi, Xlo, r, w, H, lane) + b[0];
         if (lane == 0 && v < range) {
             const int q = atomicAdd(count2, 1);
+            if (3 * q + 2 >= m) { count2[2] = 1; continue; }            // the forward-difference pass has m rows: overflow flag ([3] of the counter block)
             atomicAdd(count2 + 1, 3);                                   // [1] = rows of the forward-difference pass
             idx2[q] = idx[r];
             pts2[3 * (size_t)q] = pts[3 * (size_t)r]; pts2[3 * (size_t)q + 1] = pts[3 * (size_t)r + 1]; pts2[3 * (size_t)q + 2] = pts[3 * (size_t)r + 2];

@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.environ.get("MIS_LIB") or os.path.join(_PKG, "libmis_b200.so")   # MIS_LIB: tuning builds only
 SOURCES = ["mis_api.cu"]
-HEADERS = ["mis_math.cuh", "mis_sort.cuh", "mis_neighbors.cuh", "mis_cluster.cuh", "mis_sdf.cuh", "mis_sdf_host.cuh"]
+HEADERS = ["mis_math.cuh", "mis_sort.cuh", "mis_neighbors.cuh", "mis_cluster.cuh", "mis_tile.cuh", "mis_sdf.cuh", "mis_sdf_host.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -58,15 +58,22 @@ def needs_build() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """nvcc -gencode arch=compute_100a,code=sm_100a ... -> libmis_b200.so, in-tree."""
-    if force or needs_build():
+    if not (force or needs_build()):
+        return LIB_PATH
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:      # torchrun ranks of one box must not run nvcc into the same file at once
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():           # another rank built it while this one waited
+            return LIB_PATH
         cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-              ["-o", LIB_PATH] + [os.path.join(_CSRC, f) for f in SOURCES]
+              ["-o", LIB_PATH + ".tmp"] + [os.path.join(_CSRC, f) for f in SOURCES]
         env = dict(os.environ)
         env.pop("CC", None)      # the image exports a gcc wrapper in CC; let nvcc pick the system gcc
         env.pop("CXX", None)
         r = subprocess.run(cmd, cwd=_CSRC, env=env, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        os.replace(LIB_PATH + ".tmp", LIB_PATH)       # a reader never sees a half-written library
         if verbose:
             print(r.stderr)
     return LIB_PATH
@@ -100,6 +107,8 @@ SYMBOLS = {
     "mis_get_fields": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _vp]),
     "mis_eval_forces": (C.c_int, [_vp, _fp, _fp, _vp]),
     "mis_accumulate_loss": (C.c_int, [_vp, _fp, _fp, _vp, _vp]),
+    "mis_set_gather_mode": (C.c_int, [_vp, C.c_int, _vp]),
+    "mis_get_gather_info": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "mis_launch_count": (C.c_longlong, [_vp]),
     "mis_profile_step": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mis_gather_next_positions": (C.c_int, [_vp, _ip, C.c_int, _fp, _vp]),

@@ -418,9 +418,21 @@ class Simulator:
         self.frame += int(n_steps)
         return a.value, b.value
 
+    def set_gather_mode(self, mode: int):
+        """0: register-tiled cluster kernels (k_deform_c / k_force_c); 1: shared-memory cell tiles (k_deform_t / k_force_t);
+        2: tiles for the deformation pass, cluster kernel for the force pass (include/mis.h)."""
+        native.check(self.L.mis_set_gather_mode(self._h, int(mode), self._st()), "mis_set_gather_mode")
+
+    def gather_info(self):
+        out = (C.c_int * 8)()
+        native.check(self.L.mis_get_gather_info(self._h, out), "mis_get_gather_info")
+        keys = ("mode", "active_cells", "max_tile", "max_cell", "cap_deform", "cap_force", "list_blocks", "block_entries")
+        return dict(zip(keys, [int(v) for v in out]))
+
     def kernel_names(self):
         """Names of the two gather kernels the step launches (what profile_step times; keys of profiles/traffic.json)."""
-        return {"k_deform": "k_deform_c", "k_force": "k_force_c"}
+        mode = self.gather_info()["mode"]
+        return {"k_deform": "k_deform_t" if mode else "k_deform_c", "k_force": "k_force_t" if mode == 1 else "k_force_c"}
 
     @property
     def launch_count(self) -> int:

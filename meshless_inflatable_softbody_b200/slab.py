@@ -386,6 +386,10 @@ class SlabSimulator:
             self.sim.step(int(n_steps))               # pushes + flag waits are inside the step graph
             self.exchanges += int(n_steps)
             self.frame += int(n_steps)
+            self._steps_since_check = getattr(self, "_steps_since_check", 0) + int(n_steps)
+            if self._steps_since_check >= 4096:       # periodic (synchronising) look at the device-side timeout flag
+                self._steps_since_check = 0
+                self._check_halo()
             return
         for _ in range(int(n_steps)):
             self.sim.step(1)
@@ -399,8 +403,17 @@ class SlabSimulator:
         self.sim.step(0)
         self._exchange()
 
+    def _check_halo(self):
+        """A flag wait that timed out (a peer died, or the ranks' call sequences diverged -- e.g. eval_forces / a re-prime on one
+        rank only) is sticky on the device and every later step runs on stale ghosts: never hand such a state out silently."""
+        if self.halo == "p2p" and self.world > 1 and not self.in_process:
+            timed_out, _ = self.sim.halo_status()
+            if timed_out:
+                raise RuntimeError(f"rank {self.rank}: a halo flag wait timed out (MIS_HALO_TIMEOUT_MS); the state after that step used stale ghost positions")
+
     def position_velocity(self):
         """(x, v) of the OWNED particles, in the order of plan.owned (ascending global id)."""
+        self._check_halo()
         x, v = self.sim.position_velocity()
         return x[: self.n_owned], v[: self.n_owned]
 
@@ -429,6 +442,11 @@ class SlabSimulator:
 
     def close(self):
         if self._mapped:
+            try:
+                self._check_halo()
+            except RuntimeError as e:          # closing must still unmap; say what happened
+                import warnings
+                warnings.warn(str(e))
             self.sim.synchronize()
             self.dist.barrier(group=self.group)       # nobody is still pushing into memory about to be unmapped
             self.sim.halo_disconnect()

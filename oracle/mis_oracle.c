@@ -43,15 +43,30 @@
 #include <omp.h>
 #endif
 
-typedef struct { float x, y, z; } v3;
-typedef struct { float m[3][3]; } m33;
+/* Working precision.  Default: float (real = wp.float32, sim.py:22).  -DORC_DOUBLE builds the same source in double
+ * (libmis_oracle_f64.so): the Taichi prototype's precision (real = ti.f64, options.py:3) and an "exact arithmetic"
+ * reference for the fp32 build.  Every literal below is exactly representable in both.                            */
+#ifdef ORC_DOUBLE
+typedef double real;
+#define R_SQRT sqrt
+#define R_FABS fabs
+#define R_TANH tanh
+#else
+typedef float real;
+#define R_SQRT sqrtf
+#define R_FABS fabsf
+#define R_TANH tanhf
+#endif
+
+typedef struct { real x, y, z; } v3;
+typedef struct { real m[3][3]; } m33;
 
 typedef struct {
-    float h;            /* sim.py:25  */
-    float damping;      /* sim.py:26  */
-    float dt;           /* sim.py:65  */
-    float k_col;        /* sim.py:68  */
-    float col_range;    /* sim.py:69  */
+    real h;            /* sim.py:25  */
+    real damping;      /* sim.py:26  */
+    real dt;           /* sim.py:65  */
+    real k_col;        /* sim.py:68  */
+    real col_range;    /* sim.py:69  */
     int   grid_x, grid_y, grid_z; /* sim.py:123-125 */
     /* variant switches (sim_taichi.py deltas); 0 = sim.py */
     int   symmetric_pair;   /* 1: f_ij uses F_j (sim_taichi.py:157)       */
@@ -59,20 +74,20 @@ typedef struct {
     int   self_density;     /* 1: rho includes j == i (sim_taichi.py:97)  */
     int   euler;            /* 1: symplectic Euler (sim_taichi.py:167-172)*/
     int   no_contact;       /* 1: no ground penalty (sim_taichi.py)       */
-    float stiff_a, stiff_b; /* stiffness factor = a - b*ratio (200,199 | 1,1) */
+    real stiff_a, stiff_b; /* stiffness factor = a - b*ratio (200,199 | 1,1) */
 } OrcParams;
 
 typedef struct {
     int n;
     OrcParams p;
     /* static */
-    v3 *x0; float *mass, *rho, *vol, *E, *nu, *mu, *lam, *design, *ratio;
+    v3 *x0; real *mass, *rho, *vol, *E, *nu, *mu, *lam, *design, *ratio;
     v3 *fext, *free_;
     /* dynamic (current frame and next frame) */
     v3 *x, *v, *xn, *vn, *fel, *feln;
     m33 *A, *F, *Rc, *Sc;
     /* hash grid (sim.py:123-127) */
-    float cell_width, cell_width_inv;
+    real cell_width, cell_width_inv;
     int *point_cell, *point_ids, *cell_start, *cell_end;
     int ncells;
     int threads;
@@ -82,29 +97,29 @@ typedef struct {
 /* ------------------------------------------------------------------ vec/mat
  * Warp's vec/mat operators, in Warp's evaluation order (mul(mat,vec) and
  * mul(mat,mat) accumulate k = 0,1,2; dot accumulates x,y,z).               */
-static inline v3 v3_make(float x, float y, float z) { v3 r = {x, y, z}; return r; }
+static inline v3 v3_make(real x, real y, real z) { v3 r = {x, y, z}; return r; }
 static inline v3 v3_sub(v3 a, v3 b) { return v3_make(a.x - b.x, a.y - b.y, a.z - b.z); }
 static inline v3 v3_add(v3 a, v3 b) { return v3_make(a.x + b.x, a.y + b.y, a.z + b.z); }
-static inline v3 v3_scale(float s, v3 a) { return v3_make(s * a.x, s * a.y, s * a.z); }
-static inline v3 v3_div(v3 a, float s) { return v3_make(a.x / s, a.y / s, a.z / s); }
+static inline v3 v3_scale(real s, v3 a) { return v3_make(s * a.x, s * a.y, s * a.z); }
+static inline v3 v3_div(v3 a, real s) { return v3_make(a.x / s, a.y / s, a.z / s); }
 static inline v3 v3_cwmul(v3 a, v3 b) { return v3_make(a.x * b.x, a.y * b.y, a.z * b.z); }
-static inline float v3_length(v3 a) { return sqrtf(a.x * a.x + a.y * a.y + a.z * a.z); }
+static inline real v3_length(v3 a) { return R_SQRT(a.x * a.x + a.y * a.y + a.z * a.z); }
 
 static inline m33 m33_zero(void) { m33 r; memset(&r, 0, sizeof r); return r; }
 static inline m33 m33_identity(void) { m33 r = m33_zero(); r.m[0][0] = r.m[1][1] = r.m[2][2] = 1.f; return r; }
 static inline m33 m33_outer(v3 a, v3 b) {
-    m33 r; const float av[3] = {a.x, a.y, a.z}, bv[3] = {b.x, b.y, b.z};
+    m33 r; const real av[3] = {a.x, a.y, a.z}, bv[3] = {b.x, b.y, b.z};
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.m[i][j] = av[i] * bv[j];
     return r;
 }
-static inline m33 m33_scale(float s, m33 a) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) a.m[i][j] = s * a.m[i][j]; return a; }
+static inline m33 m33_scale(real s, m33 a) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) a.m[i][j] = s * a.m[i][j]; return a; }
 static inline m33 m33_add(m33 a, m33 b) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) a.m[i][j] = a.m[i][j] + b.m[i][j]; return a; }
 static inline m33 m33_sub(m33 a, m33 b) { for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) a.m[i][j] = a.m[i][j] - b.m[i][j]; return a; }
 static inline m33 m33_transpose(m33 a) { m33 r; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.m[i][j] = a.m[j][i]; return r; }
 static inline m33 m33_mul(m33 a, m33 b) {
     m33 r;
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
-        float s = a.m[i][0] * b.m[0][j];
+        real s = a.m[i][0] * b.m[0][j];
         s = s + a.m[i][1] * b.m[1][j];
         s = s + a.m[i][2] * b.m[2][j];
         r.m[i][j] = s;
@@ -112,24 +127,24 @@ static inline m33 m33_mul(m33 a, m33 b) {
     return r;
 }
 static inline v3 m33_mulv(m33 a, v3 b) {
-    float r[3];
+    real r[3];
     for (int i = 0; i < 3; i++) {
-        float s = a.m[i][0] * b.x;
+        real s = a.m[i][0] * b.x;
         s = s + a.m[i][1] * b.y;
         s = s + a.m[i][2] * b.z;
         r[i] = s;
     }
     return v3_make(r[0], r[1], r[2]);
 }
-static inline float m33_trace(m33 a) { return a.m[0][0] + a.m[1][1] + a.m[2][2]; }
+static inline real m33_trace(m33 a) { return a.m[0][0] + a.m[1][1] + a.m[2][2]; }
 
 /* ------------------------------------------------------------------ kernels */
-#define ORC_PI 3.14159265358979323846f   /* real(wp.pi) */
+#define ORC_PI ((real)3.14159265358979323846)   /* real(wp.pi) */
 
 /* sim.py:133-141 */
-static inline float W_kernel(v3 xij, float h) {
-    float q = v3_length(xij) / h;
-    float ret = 0.f;
+static inline real W_kernel(v3 xij, real h) {
+    real q = v3_length(xij) / h;
+    real ret = 0.f;
     if (q < 1.f) {
         ret = 1.f / (ORC_PI * h * h * h) * (1.f - 1.5f * q * q + 0.75f * q * q * q);
     } else if (q >= 1.f && q < 2.f) {
@@ -139,15 +154,15 @@ static inline float W_kernel(v3 xij, float h) {
 }
 
 /* sim.py:143-151 */
-static inline v3 nabla_W_kernel(v3 xij, float h) {
-    float q = v3_length(xij) / h;
+static inline v3 nabla_W_kernel(v3 xij, real h) {
+    real q = v3_length(xij) / h;
     v3 ret = v3_make(0.f, 0.f, 0.f);
     if (q < 1.f) {
         v3 a = v3_div(v3_div(v3_scale(-3.f, xij), h), h);
         v3 b = v3_div(v3_div(v3_scale(0.75f * 3.f * q, xij), h), h);
         ret = v3_scale(1.f / (ORC_PI * h * h * h), v3_add(a, b));
     } else if (q >= 1.f && q < 2.f) {
-        float c = 1.f / (4.f * ORC_PI * h * h * h) * -3.f * (2.f - q) * (2.f - q);
+        real c = 1.f / (4.f * ORC_PI * h * h * h) * -3.f * (2.f - q) * (2.f - q);
         ret = v3_div(v3_scale(c, xij), q * h * h);
     }
     return ret;
@@ -163,34 +178,34 @@ static inline v3 nabla_W_kernel(v3 xij, float h) {
  * decomposition to fp32 round-off.  The CUDA path implements the same
  * sequence; tests compare the two within tolerance, not bitwise.            */
 #define ORC_JACOBI_SWEEPS 6
-static inline void jacobi_rot(float S[3][3], float V[3][3], int p, int q) {
-    float apq = S[p][q];
-    if (fabsf(apq) <= 1e-30f) return;
-    float theta = (S[q][q] - S[p][p]) / (2.f * apq);
-    float t = 1.f / (fabsf(theta) + sqrtf(theta * theta + 1.f));
+static inline void jacobi_rot(real S[3][3], real V[3][3], int p, int q) {
+    real apq = S[p][q];
+    if (R_FABS(apq) <= 1e-30f) return;
+    real theta = (S[q][q] - S[p][p]) / (2.f * apq);
+    real t = 1.f / (R_FABS(theta) + R_SQRT(theta * theta + 1.f));
     if (theta < 0.f) t = -t;
-    float c = 1.f / sqrtf(t * t + 1.f);
-    float s = t * c;
+    real c = 1.f / R_SQRT(t * t + 1.f);
+    real s = t * c;
     /* S <- J^T S J with J = [[c, s], [-s, c]] on (p,q) */
-    float spp = S[p][p], sqq = S[q][q];
+    real spp = S[p][p], sqq = S[q][q];
     S[p][p] = spp - t * apq;
     S[q][q] = sqq + t * apq;
     S[p][q] = 0.f; S[q][p] = 0.f;
     int r = 3 - p - q;
-    float srp = S[r][p], srq = S[r][q];
+    real srp = S[r][p], srq = S[r][q];
     S[r][p] = c * srp - s * srq; S[p][r] = S[r][p];
     S[r][q] = s * srp + c * srq; S[q][r] = S[r][q];
     for (int k = 0; k < 3; k++) {
-        float vkp = V[k][p], vkq = V[k][q];
+        real vkp = V[k][p], vkq = V[k][q];
         V[k][p] = c * vkp - s * vkq;
         V[k][q] = s * vkp + c * vkq;
     }
 }
 
 static m33 polar_rotation(m33 Am) {
-    float S[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    real S[3][3], V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
-        float s = Am.m[0][i] * Am.m[0][j];
+        real s = Am.m[0][i] * Am.m[0][j];
         s = s + Am.m[1][i] * Am.m[1][j];
         s = s + Am.m[2][i] * Am.m[2][j];
         S[i][j] = s;
@@ -201,9 +216,9 @@ static m33 polar_rotation(m33 Am) {
         jacobi_rot(S, V, 1, 2);
     }
     /* B = A V, column norms^2 */
-    float B[3][3], nrm[3];
+    real B[3][3], nrm[3];
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
-        float s = Am.m[i][0] * V[0][j];
+        real s = Am.m[i][0] * V[0][j];
         s = s + Am.m[i][1] * V[1][j];
         s = s + Am.m[i][2] * V[2][j];
         B[i][j] = s;
@@ -212,40 +227,40 @@ static m33 polar_rotation(m33 Am) {
     /* sort columns by descending norm; a swap negates one column so det V stays +1 */
 #define ORC_CSWAP(a, b)                                                           \
     if (nrm[a] < nrm[b]) {                                                        \
-        float tn = nrm[a]; nrm[a] = nrm[b]; nrm[b] = tn;                          \
+        real tn = nrm[a]; nrm[a] = nrm[b]; nrm[b] = tn;                          \
         for (int k = 0; k < 3; k++) {                                             \
-            float tb = B[k][a]; B[k][a] = B[k][b]; B[k][b] = -tb;                 \
-            float tv = V[k][a]; V[k][a] = V[k][b]; V[k][b] = -tv;                 \
+            real tb = B[k][a]; B[k][a] = B[k][b]; B[k][b] = -tb;                 \
+            real tv = V[k][a]; V[k][a] = V[k][b]; V[k][b] = -tv;                 \
         }                                                                         \
     }
     ORC_CSWAP(0, 1) ORC_CSWAP(0, 2) ORC_CSWAP(1, 2)
 #undef ORC_CSWAP
     /* U: Gram-Schmidt on the two dominant columns, third = cross (det U = +1) */
-    float U[3][3];
-    float n0 = sqrtf(nrm[0]);
+    real U[3][3];
+    real n0 = R_SQRT(nrm[0]);
     if (!(n0 > 1e-30f)) return m33_identity();
-    float u0[3] = {B[0][0] / n0, B[1][0] / n0, B[2][0] / n0};
-    float d = u0[0] * B[0][1] + u0[1] * B[1][1] + u0[2] * B[2][1];
-    float w1[3] = {B[0][1] - d * u0[0], B[1][1] - d * u0[1], B[2][1] - d * u0[2]};
-    float n1 = sqrtf(w1[0] * w1[0] + w1[1] * w1[1] + w1[2] * w1[2]);
-    float u1[3];
+    real u0[3] = {B[0][0] / n0, B[1][0] / n0, B[2][0] / n0};
+    real d = u0[0] * B[0][1] + u0[1] * B[1][1] + u0[2] * B[2][1];
+    real w1[3] = {B[0][1] - d * u0[0], B[1][1] - d * u0[1], B[2][1] - d * u0[2]};
+    real n1 = R_SQRT(w1[0] * w1[0] + w1[1] * w1[1] + w1[2] * w1[2]);
+    real u1[3];
     if (n1 > 1e-30f) {
         u1[0] = w1[0] / n1; u1[1] = w1[1] / n1; u1[2] = w1[2] / n1;
     } else {
         /* rank-1 A: any unit vector orthogonal to u0 */
-        int k = (fabsf(u0[0]) <= fabsf(u0[1]) && fabsf(u0[0]) <= fabsf(u0[2])) ? 0
-              : (fabsf(u0[1]) <= fabsf(u0[2]) ? 1 : 2);
-        float e[3] = {0, 0, 0}; e[k] = 1.f;
-        float dd = u0[k];
-        float ww[3] = {e[0] - dd * u0[0], e[1] - dd * u0[1], e[2] - dd * u0[2]};
-        float nn = sqrtf(ww[0] * ww[0] + ww[1] * ww[1] + ww[2] * ww[2]);
+        int k = (R_FABS(u0[0]) <= R_FABS(u0[1]) && R_FABS(u0[0]) <= R_FABS(u0[2])) ? 0
+              : (R_FABS(u0[1]) <= R_FABS(u0[2]) ? 1 : 2);
+        real e[3] = {0, 0, 0}; e[k] = 1.f;
+        real dd = u0[k];
+        real ww[3] = {e[0] - dd * u0[0], e[1] - dd * u0[1], e[2] - dd * u0[2]};
+        real nn = R_SQRT(ww[0] * ww[0] + ww[1] * ww[1] + ww[2] * ww[2]);
         u1[0] = ww[0] / nn; u1[1] = ww[1] / nn; u1[2] = ww[2] / nn;
     }
-    float u2[3] = {u0[1] * u1[2] - u0[2] * u1[1], u0[2] * u1[0] - u0[0] * u1[2], u0[0] * u1[1] - u0[1] * u1[0]};
+    real u2[3] = {u0[1] * u1[2] - u0[2] * u1[1], u0[2] * u1[0] - u0[0] * u1[2], u0[0] * u1[1] - u0[1] * u1[0]};
     for (int k = 0; k < 3; k++) { U[k][0] = u0[k]; U[k][1] = u1[k]; U[k][2] = u2[k]; }
     m33 R;
     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
-        float s = U[i][0] * V[j][0];
+        real s = U[i][0] * V[j][0];
         s = s + U[i][1] * V[j][1];
         s = s + U[i][2] * V[j][2];
         R.m[i][j] = s;
@@ -260,7 +275,7 @@ static inline m33 compute_R_i(const Orc *o, m33 A) {
 }
 
 /* sim.py:212-216 */
-static inline m33 compute_sigma(const Orc *o, m33 F, float mu, float lam, float ratio) {
+static inline m33 compute_sigma(const Orc *o, m33 F, real mu, real lam, real ratio) {
     m33 E = m33_scale(0.5f, m33_sub(m33_mul(m33_transpose(F), F), m33_identity()));
     m33 s = m33_add(m33_scale(2.f * mu, E), m33_scale(lam * m33_trace(E), m33_identity()));
     return m33_scale(o->p.stiff_a - ratio * o->p.stiff_b, s);   /* mat * scalar: same products */
@@ -270,7 +285,7 @@ static inline m33 compute_sigma(const Orc *o, m33 F, float mu, float lam, float 
 static inline v3 collision_penalty(const Orc *o, v3 pos) {
     v3 pen = v3_make(0.f, 0.f, 0.f);
     if (!o->p.no_contact && pos.y < o->p.col_range) {
-        float delta = o->p.col_range - pos.y;
+        real delta = o->p.col_range - pos.y;
         pen.y = delta * delta * o->p.k_col;
     }
     return pen;
@@ -312,7 +327,7 @@ static void hg_build(Orc *o) {
 }
 
 typedef struct { int xs, ys, zs, xe, ye, ze; } HgQuery;
-static inline HgQuery hg_query(const Orc *o, v3 pos, float radius) {
+static inline HgQuery hg_query(const Orc *o, v3 pos, real radius) {
     HgQuery q;
     q.xs = (int)((pos.x - radius) * o->cell_width_inv);
     q.ys = (int)((pos.y - radius) * o->cell_width_inv);
@@ -351,14 +366,14 @@ static int hg_candidates(const Orc *o, v3 pos, int *cand, int cap) {
 /* ------------------------------------------------------------------ passes */
 /* sim.py:154-167 */
 static void compute_v_i(Orc *o) {
-    int n = o->n; float h = o->p.h;
+    int n = o->n; real h = o->p.h;
 #pragma omp parallel num_threads(o->threads)
     {
         int *cand = (int *)malloc(ORC_MAX_CAND * sizeof(int));
 #pragma omp for schedule(dynamic, 64)
         for (int i = 0; i < n; i++) {
             v3 x = o->x0[i];
-            float r = 0.f;
+            real r = 0.f;
             int m = hg_candidates(o, x, cand, ORC_MAX_CAND);
             for (int c = 0; c < m; c++) {
                 int index = cand[c];
@@ -374,7 +389,7 @@ static void compute_v_i(Orc *o) {
 
 /* sim.py:170-183 */
 static void compute_A_pq(Orc *o, const v3 *pos, m33 *Aout) {
-    int n = o->n; float h = o->p.h;
+    int n = o->n; real h = o->p.h;
 #pragma omp parallel num_threads(o->threads)
     {
         int *cand = (int *)malloc(ORC_MAX_CAND * sizeof(int));
@@ -386,7 +401,7 @@ static void compute_A_pq(Orc *o, const v3 *pos, m33 *Aout) {
             for (int c = 0; c < m; c++) {
                 int j = cand[c];
                 if (j != i) {
-                    float w = W_kernel(v3_sub(x0, o->x0[j]), h);
+                    real w = W_kernel(v3_sub(x0, o->x0[j]), h);
                     a = m33_add(a, m33_scale(w * o->mass[j], m33_outer(v3_sub(pos[j], x), v3_sub(o->x0[j], x0))));
                 }
             }
@@ -398,7 +413,7 @@ static void compute_A_pq(Orc *o, const v3 *pos, m33 *Aout) {
 
 /* sim.py:193-209 */
 static void compute_nabla_u(Orc *o, const v3 *pos, const m33 *Ain, m33 *Fout) {
-    int n = o->n; float h = o->p.h;
+    int n = o->n; real h = o->p.h;
 #pragma omp parallel num_threads(o->threads)
     {
         int *cand = (int *)malloc(ORC_MAX_CAND * sizeof(int));
@@ -425,7 +440,7 @@ static void compute_nabla_u(Orc *o, const v3 *pos, const m33 *Ain, m33 *Fout) {
 
 /* sim.py:218-235.  mode 0 = faithful (as written), mode 1 = cached R_j, S_j. */
 static void compute_elastic_forces(Orc *o, const m33 *Ain, const m33 *Fin, v3 *fout, int mode) {
-    int n = o->n; float h = o->p.h;
+    int n = o->n; real h = o->p.h;
     if (mode == 1) {
 #pragma omp parallel for schedule(static) num_threads(o->threads)
         for (int i = 0; i < n; i++) {
@@ -471,7 +486,7 @@ static void compute_elastic_forces(Orc *o, const m33 *Ain, const m33 *Fin, v3 *f
 
 /* sim.py:247-251 */
 static void part_1(Orc *o) {
-    float dt = o->p.dt, damping = o->p.damping;
+    real dt = o->p.dt, damping = o->p.damping;
 #pragma omp parallel for schedule(static) num_threads(o->threads)
     for (int i = 0; i < o->n; i++) {
         v3 force = v3_add(v3_sub(v3_add(o->fext[i], o->fel[i]), v3_scale(damping, o->v[i])), collision_penalty(o, o->x[i]));
@@ -481,7 +496,7 @@ static void part_1(Orc *o) {
 }
 /* sim.py:253-258 */
 static void part_2(Orc *o) {
-    float dt = o->p.dt, damping = o->p.damping;
+    real dt = o->p.dt, damping = o->p.damping;
 #pragma omp parallel for schedule(static) num_threads(o->threads)
     for (int i = 0; i < o->n; i++) {
         v3 f1 = v3_add(v3_sub(v3_add(o->fext[i], o->fel[i]), v3_scale(damping, o->v[i])), collision_penalty(o, o->x[i]));
@@ -492,7 +507,7 @@ static void part_2(Orc *o) {
 }
 /* sim_taichi.py:167-172 (advance; damping force folded in, sim_taichi.py:161-164) */
 static void advance_euler(Orc *o) {
-    float dt = o->p.dt, damping = o->p.damping;
+    real dt = o->p.dt, damping = o->p.damping;
 #pragma omp parallel for schedule(static) num_threads(o->threads)
     for (int i = 0; i < o->n; i++) {
         v3 force = v3_add(v3_add(o->fext[i], o->fel[i]), v3_scale(-damping, o->v[i]));
@@ -504,7 +519,7 @@ static void advance_euler(Orc *o) {
 /* ------------------------------------------------------------------ C API */
 #define ORC_ALLOC(T, cnt) ((T *)calloc((size_t)(cnt), sizeof(T)))
 
-Orc *orc_create(int n, const float *x0, const OrcParams *p, int threads) {
+Orc *orc_create(int n, const real *x0, const OrcParams *p, int threads) {
     Orc *o = ORC_ALLOC(Orc, 1);
     o->n = n; o->p = *p;
     if (o->p.grid_x < 1) o->p.grid_x = 1;
@@ -517,9 +532,9 @@ Orc *orc_create(int n, const float *x0, const OrcParams *p, int threads) {
     o->threads = 1; (void)threads;
 #endif
     o->x0 = ORC_ALLOC(v3, n); memcpy(o->x0, x0, sizeof(v3) * (size_t)n);
-    o->mass = ORC_ALLOC(float, n); o->rho = ORC_ALLOC(float, n); o->vol = ORC_ALLOC(float, n);
-    o->E = ORC_ALLOC(float, n); o->nu = ORC_ALLOC(float, n); o->mu = ORC_ALLOC(float, n); o->lam = ORC_ALLOC(float, n);
-    o->design = ORC_ALLOC(float, n); o->ratio = ORC_ALLOC(float, n);
+    o->mass = ORC_ALLOC(real, n); o->rho = ORC_ALLOC(real, n); o->vol = ORC_ALLOC(real, n);
+    o->E = ORC_ALLOC(real, n); o->nu = ORC_ALLOC(real, n); o->mu = ORC_ALLOC(real, n); o->lam = ORC_ALLOC(real, n);
+    o->design = ORC_ALLOC(real, n); o->ratio = ORC_ALLOC(real, n);
     o->fext = ORC_ALLOC(v3, n); o->free_ = ORC_ALLOC(v3, n);
     o->x = ORC_ALLOC(v3, n); o->v = ORC_ALLOC(v3, n); o->xn = ORC_ALLOC(v3, n); o->vn = ORC_ALLOC(v3, n);
     o->fel = ORC_ALLOC(v3, n); o->feln = ORC_ALLOC(v3, n);
@@ -544,34 +559,34 @@ void orc_set_order(Orc *o, int order) { o->order = order; }
 /* sim.py:288-300: mu, lam from per-particle E, nu */
 static void lame(Orc *o) {
     for (int i = 0; i < o->n; i++) {
-        float E = o->E[i], nu = o->nu[i];
+        real E = o->E[i], nu = o->nu[i];
         o->mu[i] = E / (2.f * (1.f + nu));
         o->lam[i] = E * nu / ((1.f + nu) * (1.f - 2.f * nu));
     }
 }
-void orc_set_youngs_modulus(Orc *o, const float *E) { memcpy(o->E, E, sizeof(float) * (size_t)o->n); lame(o); }
-void orc_set_poisson_ratio(Orc *o, const float *nu) { memcpy(o->nu, nu, sizeof(float) * (size_t)o->n); lame(o); }
+void orc_set_youngs_modulus(Orc *o, const real *E) { memcpy(o->E, E, sizeof(real) * (size_t)o->n); lame(o); }
+void orc_set_poisson_ratio(Orc *o, const real *nu) { memcpy(o->nu, nu, sizeof(real) * (size_t)o->n); lame(o); }
 /* sim.py:306-308 */
-void orc_set_mass(Orc *o, const float *m) { memcpy(o->mass, m, sizeof(float) * (size_t)o->n); compute_v_i(o); }
+void orc_set_mass(Orc *o, const real *m) { memcpy(o->mass, m, sizeof(real) * (size_t)o->n); compute_v_i(o); }
 /* sim.py:279-286 */
-void orc_set_external_forces(Orc *o, const float *f) { memcpy(o->fext, f, sizeof(v3) * (size_t)o->n); }
-void orc_set_free_points(Orc *o, const float *d) { memcpy(o->free_, d, sizeof(v3) * (size_t)o->n); }
+void orc_set_external_forces(Orc *o, const real *f) { memcpy(o->fext, f, sizeof(v3) * (size_t)o->n); }
+void orc_set_free_points(Orc *o, const real *d) { memcpy(o->free_, d, sizeof(v3) * (size_t)o->n); }
 /* sim.py:107-110 (tanh_k = 3; sim_taichi.py:81 uses 5) */
-void orc_set_design(Orc *o, const float *x, float tanh_k) {
-    memcpy(o->design, x, sizeof(float) * (size_t)o->n);
-    for (int i = 0; i < o->n; i++) o->ratio[i] = 0.5f * tanhf(tanh_k * x[i]) + 0.5f;
+void orc_set_design(Orc *o, const real *x, real tanh_k) {
+    memcpy(o->design, x, sizeof(real) * (size_t)o->n);
+    for (int i = 0; i < o->n; i++) o->ratio[i] = 0.5f * R_TANH(tanh_k * x[i]) + 0.5f;
 }
-void orc_set_ratio(Orc *o, const float *ratio) { memcpy(o->ratio, ratio, sizeof(float) * (size_t)o->n); }
+void orc_set_ratio(Orc *o, const real *ratio) { memcpy(o->ratio, ratio, sizeof(real) * (size_t)o->n); }
 
 /* sim.py:261-266 startup + sim.py:349-351 frame-0 priming */
-void orc_startup(Orc *o, const float *v0, int mode) {
+void orc_startup(Orc *o, const real *v0, int mode) {
     for (int i = 0; i < o->n; i++) { o->x[i] = o->x0[i]; o->v[i] = v3_make(v0[0], v0[1], v0[2]); }
     compute_A_pq(o, o->x, o->A);
     compute_nabla_u(o, o->x, o->A, o->F);
     compute_elastic_forces(o, o->A, o->F, o->fel, mode);
 }
 /* restart from an arbitrary state (x, v): re-primes forces at x */
-void orc_set_state(Orc *o, const float *x, const float *v, int mode) {
+void orc_set_state(Orc *o, const real *x, const real *v, int mode) {
     memcpy(o->x, x, sizeof(v3) * (size_t)o->n); memcpy(o->v, v, sizeof(v3) * (size_t)o->n);
     compute_A_pq(o, o->x, o->A);
     compute_nabla_u(o, o->x, o->A, o->F);
@@ -603,7 +618,7 @@ void orc_step(Orc *o, int n_steps, int mode) {
 }
 
 /* one force evaluation at an arbitrary configuration (no integration) */
-void orc_eval(Orc *o, const float *pos, int mode, float *A_out, float *R_out, float *F_out, float *S_out, float *f_out) {
+void orc_eval(Orc *o, const real *pos, int mode, real *A_out, real *R_out, real *F_out, real *S_out, real *f_out) {
     int n = o->n;
     v3 *P = ORC_ALLOC(v3, n); memcpy(P, pos, sizeof(v3) * (size_t)n);
     m33 *A = ORC_ALLOC(m33, n), *F = ORC_ALLOC(m33, n); v3 *f = ORC_ALLOC(v3, n);
@@ -620,23 +635,23 @@ void orc_eval(Orc *o, const float *pos, int mode, float *A_out, float *R_out, fl
     free(P); free(A); free(F); free(f);
 }
 
-void orc_get_state(const Orc *o, float *x, float *v) {
+void orc_get_state(const Orc *o, real *x, real *v) {
     if (x) memcpy(x, o->x, sizeof(v3) * (size_t)o->n);
     if (v) memcpy(v, o->v, sizeof(v3) * (size_t)o->n);
 }
-void orc_get_forces(const Orc *o, float *fel) { memcpy(fel, o->fel, sizeof(v3) * (size_t)o->n); }
-void orc_get_fields(const Orc *o, float *A, float *F) {
+void orc_get_forces(const Orc *o, real *fel) { memcpy(fel, o->fel, sizeof(v3) * (size_t)o->n); }
+void orc_get_fields(const Orc *o, real *A, real *F) {
     if (A) memcpy(A, o->A, sizeof(m33) * (size_t)o->n);
     if (F) memcpy(F, o->F, sizeof(m33) * (size_t)o->n);
 }
-void orc_get_volume(const Orc *o, float *rho, float *vol) {
-    if (rho) memcpy(rho, o->rho, sizeof(float) * (size_t)o->n);
-    if (vol) memcpy(vol, o->vol, sizeof(float) * (size_t)o->n);
+void orc_get_volume(const Orc *o, real *rho, real *vol) {
+    if (rho) memcpy(rho, o->rho, sizeof(real) * (size_t)o->n);
+    if (vol) memcpy(vol, o->vol, sizeof(real) * (size_t)o->n);
 }
-void orc_get_lame(const Orc *o, float *mu, float *lam, float *ratio) {
-    if (mu) memcpy(mu, o->mu, sizeof(float) * (size_t)o->n);
-    if (lam) memcpy(lam, o->lam, sizeof(float) * (size_t)o->n);
-    if (ratio) memcpy(ratio, o->ratio, sizeof(float) * (size_t)o->n);
+void orc_get_lame(const Orc *o, real *mu, real *lam, real *ratio) {
+    if (mu) memcpy(mu, o->mu, sizeof(real) * (size_t)o->n);
+    if (lam) memcpy(lam, o->lam, sizeof(real) * (size_t)o->n);
+    if (ratio) memcpy(ratio, o->ratio, sizeof(real) * (size_t)o->n);
 }
 /* hash-grid structures: per-particle linear cell index, unwrapped integer cell
  * coordinates, the cell-sorted particle order                               */
@@ -662,7 +677,7 @@ long long orc_neighbor_lists(const Orc *o, int *counts, long long *offsets, int 
         for (int c = 0; c < m; c++) {
             int j = cand[c];
             if (j == i) continue;
-            float q = v3_length(v3_sub(o->x0[i], o->x0[j])) / o->p.h;
+            real q = v3_length(v3_sub(o->x0[i], o->x0[j])) / o->p.h;
             if (q < 2.f) cand[k++] = j;
         }
         qsort(cand, (size_t)k, sizeof(int), cmp_int);
@@ -685,10 +700,10 @@ long long orc_candidate_count(const Orc *o) {
 }
 
 /* stand-alone helpers exported for the known-answer tests */
-float orc_W(float x, float y, float z, float h) { return W_kernel(v3_make(x, y, z), h); }
-void orc_nabla_W(float x, float y, float z, float h, float *out) { v3 g = nabla_W_kernel(v3_make(x, y, z), h); out[0] = g.x; out[1] = g.y; out[2] = g.z; }
-void orc_polar(const float *A, float *R) { m33 a, r; memcpy(&a, A, sizeof a); r = polar_rotation(a); memcpy(R, &r, sizeof r); }
-void orc_sigma(const float *F, float mu, float lam, float ratio, float *S) {
+real orc_W(real x, real y, real z, real h) { return W_kernel(v3_make(x, y, z), h); }
+void orc_nabla_W(real x, real y, real z, real h, real *out) { v3 g = nabla_W_kernel(v3_make(x, y, z), h); out[0] = g.x; out[1] = g.y; out[2] = g.z; }
+void orc_polar(const real *A, real *R) { m33 a, r; memcpy(&a, A, sizeof a); r = polar_rotation(a); memcpy(R, &r, sizeof r); }
+void orc_sigma(const real *F, real mu, real lam, real ratio, real *S) {
     Orc tmp; memset(&tmp, 0, sizeof tmp); tmp.p.stiff_a = 200.f; tmp.p.stiff_b = 199.f;
     m33 f, s; memcpy(&f, F, sizeof f); s = compute_sigma(&tmp, f, mu, lam, ratio); memcpy(S, &s, sizeof s);
 }

@@ -46,9 +46,9 @@ def taichi_fixture():
     return _load("sim_taichi_n*.npz")[0]
 
 
-def taichi_oracle(t, order=0):
+def taichi_oracle(t, order=0, precision="f32"):
     x0 = t["x0"].astype(np.float32)
-    o = co.Oracle(x0, h=float(t["h"]), dt=float(t["time_step"]), damping=float(t["damping"]), variant="taichi")
+    o = co.Oracle(x0, h=float(t["h"]), dt=float(t["time_step"]), damping=float(t["damping"]), variant="taichi", precision=precision)
     o.set_order(order)
     o.set_external_forces(t["external_forces"])
     o.set_free_points(t["free_points"])
@@ -164,3 +164,33 @@ def test_taichi_prototype_matches_reference_source():
     assert np.abs(e["f"] - ref).max() <= 2e-4 * np.abs(ref).max()
     assert np.abs(e["F"] - t[f"def_grad_{f}"]).max() <= 2e-6
     assert np.abs(e["S"] - t[f"sigma_{f}"]).max() <= 2e-4 * np.abs(t[f"sigma_{f}"]).max()
+
+
+def test_taichi_prototype_in_double_matches_reference_source_tightly():
+    """The same oracle source built with real = double (options.py:3: real = ti.f64): the prototype's trajectory to ~1e-13."""
+    t = taichi_fixture()
+    a = taichi_oracle(t, precision="f64")
+    rho, vol = a.volume()
+    assert rho.dtype == np.float64
+    assert np.abs(rho - t["rho_i"]).max() <= 1e-13 * rho.max() and np.abs(vol - t["volume_i"]).max() <= 1e-13 * vol.max()
+    a.startup((0.0, 0.0, 0.0))
+    done = 0
+    for f in [int(f) for f in t["save_frames"]]:
+        if f == 0:
+            continue
+        a.step(f - done); done = f
+        assert np.abs(a.position() - t[f"position_{f}"]).max() <= 1e-13, f
+        assert np.abs(a.velocity() - t[f"velocity_{f}"]).max() <= 1e-11, f
+    e = a.eval(t[f"position_{done}"])
+    for k, name, tol in (("F", "def_grad", 1e-13), ("S", "sigma", 1e-9), ("f", "elastic_forces", 1e-12)):
+        assert np.abs(e[k] - t[f"{name}_{done}"]).max() <= tol * max(1.0, np.abs(t[f"{name}_{done}"]).max()), name
+
+
+def test_double_build_of_the_oracle_matches_the_fp64_fixture_of_sim_py():
+    """real = double on the sim.py path: A_pq, R (Jacobi polar here, LAPACK in the fixture), def_grad, S, force to ~1e-10 relative."""
+    g = fields_fixture()
+    o = make_oracle(g["x0"], precision="f64")
+    e = o.eval(g["xdef"])
+    for k, name in (("A", "A_pq"), ("R", "R"), ("F", "def_grad"), ("S", "S"), ("f", "elastic_forces")):
+        ref = g[f"f64_{name}"]
+        assert np.abs(e[k] - ref).max() <= 1e-9 * np.abs(ref).max(), (name, np.abs(e[k] - ref).max() / np.abs(ref).max())

@@ -61,6 +61,8 @@ typedef struct MisParams {
     int   two_pass_deform;   /* 1: def_grad with the reference's two-loop order (sim.py:203-208)  */
     int   cluster_size;      /* 1, 2 or 4 consecutive cell-sorted particles share one union
                                 neighbour list and every gathered record (0 = default 2)       */
+    int   fp64;              /* 1: the scene's state and arithmetic are double (options.py:3 real = ti.f64): the
+                                reference-order kernels of mis_ref.cuh step it; see mis_set_f64 / mis_get_f64 */
 } MisParams;
 
 typedef struct MisNeighborInfo {
@@ -209,6 +211,29 @@ int mis_set_gather_mode(MisSim* sim, int mode, void* stream);
 /* out[0] mode in effect, [1] active cells, [2] largest tile (particles), [3] largest cell, [4] / [5] tile capacity of the
  * deform / force instantiation, [6] list blocks, [7] entries per block                                                       */
 int mis_get_gather_info(MisSim* sim, int out[8]);
+/* fp64 scenes (MisParams.fp64 = 1; sim_taichi.py runs in ti.f64, options.py:3).  The float setters / getters above keep
+ * working (values converted exactly / rounded); these two move doubles, n x dim in caller order:
+ *   what  0 x0 (3)  1 mass  2 youngs_modulus  3 poisson_ratio  4 design x  5 external_forces (3)  6 free_points (3)
+ *         7 position (3)  8 velocity (3)                                              -- settable and gettable
+ *         9 elastic_forces (3)  10 volume  11 rho  12 def_grad (9)  13 stress S (9)  14 rotation R (9)  15 A_pq (9)  -- get only
+ * Not available for fp64 scenes: obstacle contact, halo plumbing, host streaming, mis_profile_step, mis_build_neighbors.      */
+int mis_set_f64(MisSim* sim, int what, const double* src_dev, void* stream);
+/* The scene constants of an fp64 scene in double (MisParams carries floats: 0.1f is not 0.1): c = { h, damping, time_step,
+ * collision_penalty_stiffness, collision_range, stiffness_a, stiffness_b, tanh_k }.  The neighbour structure keeps the fp32 h
+ * (a pair the two disagree on lies at q = 2, where W and nabla_W vanish).                                                    */
+int mis_set_constants_f64(MisSim* sim, const double c[8]);
+/* startup (sim.py:261-266 / sim_taichi.py:203-207) with the initial velocity in double                                       */
+int mis_startup_f64(MisSim* sim, const double v0[3], void* stream);
+int mis_get_f64(MisSim* sim, int what, double* dst_dev, void* stream);
+/* Reverse pass of the rollout: diff_sim(compute_grad=True), sim.py:341-372 -- startup (with the initial velocity of the last
+ * mis_startup), `frames` steps of the velocity-Verlet loop, compute_loss (sim.py:269-273) against target t (t = 0 ..
+ * n_targets-1; n x 3 fp32 each, caller order, target t at offset t * 3n) at frame (frames / n_targets) * (t + 1), then the
+ * adjoint sweep (wp.Tape.backward, sim.py:371).  Returns the loss (host) and d loss / d design x (sim.py:372 x.grad; n values,
+ * caller order) as fp32 and/or fp64 (either pointer may be NULL).  The reference keeps every frame for its tape; here the
+ * trajectory is checkpointed every `checkpoint_every` frames (0 = sqrt(frames)) and recomputed segment by segment.  Arithmetic:
+ * the scene's precision (fp32, or fp64 with MisParams.fp64).  Synchronises the host; the scene must be re-started afterwards.   */
+int mis_rollout_grad(MisSim* sim, int frames, int n_targets, const float* target_x_dev, const float* target_v_dev,
+                     int checkpoint_every, double* loss_host, float* grad_dev, double* grad64_dev, void* stream);
 /* number of kernels this sim has launched so far (bench.py's gpu_launches)           */
 long long mis_launch_count(MisSim* sim);
 /* Measurement aid: n_steps steps with a CUDA event pair around every kernel launch on

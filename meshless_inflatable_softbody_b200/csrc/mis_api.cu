@@ -89,6 +89,10 @@ struct MisSim {
     double* loss_partial = nullptr;   // block partial sums of mis_accumulate_loss
     float* stage = nullptr;           // n*6 device staging for host-buffer variants
     int cur = 0;
+    float* raw_in = nullptr;          // 3n: Young's modulus, Poisson ratio, design x as given (slot order): inputs of the precision-templated engine
+    double v0[3] = {0.0, 0.0, 0.0};  // initial velocity of the last mis_startup / mis_startup_f64
+    void* ref32 = nullptr;            // RefEngine<float>*  (mis_rollout_grad on an fp32 scene)
+    void* ref64 = nullptr;            // RefEngine<double>* (MisParams.fp64: the whole scene steps in double)
     cudaError_t enqueue_err = cudaSuccess;    // first error of a launch inside an enqueue_* helper (reported by the calling entry point)
     bool built = false, mass_set = false, material_set = false, started = false, dirty = true;
     bool forces_only = false;         // dirty because of fext / free_points alone: the stored elastic force is still valid
@@ -110,8 +114,9 @@ struct MisSim {
     // the contact chain only reads the positions of the new frame, like k_deform_c: it runs beside it on a forked,
     // higher-priority stream (a parallel branch of the step graph) and joins before k_force_c
     cudaStream_t side_stream = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_chain = nullptr;
     bool serial_contact = false;
+    bool contact_first = true;                // MIS_CONTACT_FIRST=0: launch the deformation kernel at once instead of behind the chain's first layer
     // fused halo push (slab-partitioned scenes)
     int2* push = nullptr;                       // per-slot destination codes
     unsigned* halo_mem = nullptr;               // [0..MIS_MAX_PEERS) flags written by the peers, [MIS_MAX_PEERS] epoch, [MIS_MAX_PEERS + 1] error
@@ -130,6 +135,11 @@ struct MisSim {
     float* sstage[2] = {nullptr, nullptr};      // n*6 each: exported position + velocity
     long long up_i = 0, down_i = 0;
 };
+
+#include "mis_ref_host.cuh"
+static inline RefEngine<double>* R64(MisSim* s) { return (RefEngine<double>*)s->ref64; }
+static inline RefEngine<float>* R32(MisSim* s) { return (RefEngine<float>*)s->ref32; }
+#define NO_FP64(what) do { if (s && s->ref64) return fail(MIS_E_UNSUPPORTED, what " is not available for an fp64 scene (MisParams.fp64)"); } while (0)
 
 static int ensure_copy_stream(MisSim* s) {
     if (s->copy_stream) return MIS_OK;
@@ -200,6 +210,7 @@ static void drop_graph(MisSim* s) {
     s->graphs.clear();
 }
 
+static int ref64_attach(MisSim* s, cudaStream_t st);
 // ------------------------------------------------------------------ create / destroy
 extern "C" int mis_create(int n, const float* x0_dev, const MisParams* params, void* stream, MisSim** out) {
     if (!out || !params || !x0_dev || n <= 0) return fail(MIS_E_INVALID, "mis_create: bad argument");
@@ -241,7 +252,7 @@ extern "C" int mis_create(int n, const float* x0_dev, const MisParams* params, v
     ALLOC(s->cl_count, N); ALLOC(s->cl_start, N + 1);
     ALLOC(s->x0m, N); ALLOC(s->xv[0], N); ALLOC(s->xv[1], N); ALLOC(s->vel, N); ALLOC(s->f1, N); ALLOC(s->fel, N);
     ALLOC(s->fext, N); ALLOC(s->freem, N); ALLOC(s->matl, N); ALLOC(s->RS, 4 * N); ALLOC(s->Fd, 3 * N); ALLOC(s->Ks, 3 * N);
-    ALLOC(s->scratch4, 2 * N); ALLOC(s->stage, 6 * N);
+    ALLOC(s->scratch4, 2 * N); ALLOC(s->stage, 6 * N); ALLOC(s->raw_in, 3 * N);
     if (s->p.keep_fields) ALLOC(s->Apq, 9 * N);
 #undef ALLOC
     cudaMemsetAsync(s->x0m, 0, N * sizeof(float4), st);
@@ -265,6 +276,7 @@ extern "C" int mis_create(int n, const float* x0_dev, const MisParams* params, v
     if (e != cudaSuccess) { int r = fail(MIS_E_CUDA, std::string("copy x0: ") + cudaGetErrorString(e)); mis_destroy(s); return r; }
     int rc = mis_build_neighbors(s, stream);
     if (rc != MIS_OK) { mis_destroy(s); return rc; }
+    if (s->p.fp64) { rc = ref64_attach(s, st); if (rc != MIS_OK) { mis_destroy(s); return rc; } }
     *out = s;
     return MIS_OK;
 }
@@ -274,7 +286,7 @@ extern "C" int mis_destroy(MisSim* s) {
     drop_graph(s);
     if (s->side_stream) {
         cudaStreamSynchronize(s->side_stream);
-        cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join);
+        cudaEventDestroy(s->ev_fork); cudaEventDestroy(s->ev_join); if (s->ev_chain) cudaEventDestroy(s->ev_chain);
         cudaStreamDestroy(s->side_stream);
     }
     if (s->copy_stream) {
@@ -291,6 +303,9 @@ extern "C" int mis_destroy(MisSim* s) {
                     s->cell_lin_sorted, s->nbr_count, s->nbr_start, s->scan_tmp, s->nbr, s->cl_count, s->cl_start, s->cl, s->x0m, s->xv[0], s->xv[1], s->vel,
                     s->f1, s->fel, s->fext, s->freem, s->matl, s->RS, s->Fd, s->Apq, s->scratch4, s->stage};
     for (void* p : ptrs) if (p) cudaFree(p);
+    if (s->ref32) { R32(s)->release(); delete R32(s); }
+    if (s->ref64) { R64(s)->release(); delete R64(s); }
+    if (s->raw_in) cudaFree(s->raw_in);
     void* tptrs[] = {s->tile.wkey, s->tile.order, s->tile.tab, s->tile.flag, s->tile.pos, s->tile.nblocks, s->tile.blk_start, s->tile.t_off, s->tile.lists, s->tile.AB, s->tile.max_dev};
     for (void* p : tptrs) if (p) cudaFree(p);
     delete s;
@@ -417,6 +432,7 @@ static bool use_tiles_f(const MisSim* s) { return s->tile.want_f && s->tile.ok &
 
 extern "C" int mis_build_neighbors(MisSim* s, void* stream) {
     if (!s) return fail(MIS_E_INVALID, "null sim");
+    if (s->ref64) return fail(MIS_E_UNSUPPORTED, "fp64 scenes keep the neighbour structure of mis_create (a rebuild is idempotent anyway: queries are on x0)");
     cudaStream_t st = (cudaStream_t)stream;
     const int n = s->n;
     const float cw = 2.f * s->p.h;            // real(2.) * h, sim.py:127
@@ -496,6 +512,138 @@ extern "C" int mis_build_neighbors(MisSim* s, void* stream) {
     return MIS_OK;
 }
 
+
+// ------------------------------------------------------------------ precision-templated engine (mis_ref.cuh)
+// statics of an engine from the fp32 scene state: x0, m, fext, free_points from the float4 arrays, E / nu / design from raw_in
+template <typename T> static void ref_pull(MisSim* s, RefEngine<T>& g, unsigned what, cudaStream_t st) {
+    const int n = s->n, b = nblk(n, 256);
+    g.s.nbr_start = s->nbr_start; g.s.nbr = s->nbr;
+    if (what & 1u) ref::kr_pull<T><<<b, 256, 0, st>>>(s->x0m, n, 0, 3, g.s.x0);
+    if (what & 2u) ref::kr_pull<T><<<b, 256, 0, st>>>(s->x0m, n, 3, 1, g.s.m);
+    if (what & 4u) {
+        ref::kr_cast<T, float><<<b, 256, 0, st>>>(s->raw_in, n, g.E);
+        ref::kr_cast<T, float><<<b, 256, 0, st>>>(s->raw_in + n, n, g.nu);
+    }
+    if (what & 8u) ref::kr_cast<T, float><<<b, 256, 0, st>>>(s->raw_in + 2 * (size_t)n, n, g.design);
+    if (what & 16u) ref::kr_pull<T><<<b, 256, 0, st>>>(s->fext, n, 0, 3, g.s.fext);
+    if (what & 32u) ref::kr_pull<T><<<b, 256, 0, st>>>(s->freem, n, 0, 3, g.s.freem);
+    if (what & (2u | 4u | 8u)) g.statics_dirty = true;
+    g.primed = false;
+}
+static int ref64_attach(MisSim* s, cudaStream_t st) {
+    if (s->p.two_pass_deform) return fail(MIS_E_UNSUPPORTED, "fp64: two_pass_deform is an fp32 tuning flag");
+    RefEngine<double>* g = new RefEngine<double>();
+    s->ref64 = g;
+    CK(ref_create(*g, s->n, s->nbr_start, s->nbr, s->p));
+    ref_pull(s, *g, 1u | 32u, st);
+    CK_LAUNCH();
+    return MIS_OK;
+}
+// the float setters of an fp64 scene forward their (exactly converted) values to the engine
+static void ref64_after_set(MisSim* s, unsigned what, cudaStream_t st) { if (s->ref64) ref_pull(s, *R64(s), what, st); }
+
+template <typename T> static T* f64_target(RefEngine<T>& g, int what, int* dim, bool* is_static) {
+    *is_static = true;
+    switch (what) {
+        case F64_X0: *dim = 3; return g.s.x0;          case F64_MASS: *dim = 1; return g.s.m;
+        case F64_YOUNGS: *dim = 1; return g.E;         case F64_POISSON: *dim = 1; return g.nu;
+        case F64_DESIGN: *dim = 1; return g.design;    case F64_EXT_FORCE: *dim = 3; return g.s.fext;
+        case F64_DIRICHLET: *dim = 3; return g.s.freem;
+        case F64_POSITION: *dim = 3; *is_static = false; return g.s.x;
+        case F64_VELOCITY: *dim = 3; *is_static = false; return g.s.v;
+        case F64_ELASTIC_FORCE: *dim = 3; *is_static = false; return g.s.fel;
+        case F64_VOLUME: *dim = 1; return g.s.vol;     case F64_RHO: *dim = 1; return g.s.rho;
+        case F64_DEF_GRAD: *dim = 9; *is_static = false; return g.s.F;   case F64_STRESS: *dim = 9; *is_static = false; return g.s.S;
+        case F64_ROTATION: *dim = 9; *is_static = false; return g.s.R;   case F64_A_PQ: *dim = 9; *is_static = false; return g.s.A;
+    }
+    return nullptr;
+}
+
+extern "C" int mis_set_constants_f64(MisSim* s, const double c[8]) {
+    if (!s || !c) return fail(MIS_E_INVALID, "null argument");
+    if (!s->ref64) return fail(MIS_E_STATE, "mis_set_constants_f64 needs a scene created with MisParams.fp64 = 1");
+    if (!(c[0] > 0.0) || !(c[2] > 0.0)) return fail(MIS_E_INVALID, "h and dt must be positive");
+    ref::RP<double>& r = R64(s)->c;
+    r.h = c[0]; r.damping = c[1]; r.dt = c[2]; r.k_col = c[3]; r.col_range = c[4]; r.stiff_a = c[5]; r.stiff_b = c[6]; r.tanh_k = c[7];
+    R64(s)->statics_dirty = true; R64(s)->primed = false;
+    return MIS_OK;
+}
+
+extern "C" int mis_set_f64(MisSim* s, int what, const double* src_dev, void* stream) {
+    if (!s || !src_dev) return fail(MIS_E_INVALID, "null argument");
+    if (!s->ref64) return fail(MIS_E_STATE, "mis_set_f64 needs a scene created with MisParams.fp64 = 1");
+    if (what < F64_X0 || what > F64_VELOCITY) return fail(MIS_E_INVALID, "mis_set_f64: `what` must be one of x0, mass, youngs, poisson, design, ext_force, dirichlet, position, velocity");
+    cudaStream_t st = (cudaStream_t)stream;
+    RefEngine<double>& g = *R64(s);
+    int dim = 0; bool stat = false;
+    double* dst = f64_target(g, what, &dim, &stat);
+    ref::kr_gather<double, double><<<nblk(s->n, 256), 256, 0, st>>>(src_dev, s->perm, s->n, dim, dst);
+    CK_LAUNCH(); s->launches++;
+    if (what == F64_X0 || what == F64_MASS || what == F64_YOUNGS || what == F64_POISSON || what == F64_DESIGN) g.statics_dirty = true;
+    if (what == F64_MASS) s->mass_set = true;
+    if (what == F64_YOUNGS || what == F64_POISSON) s->material_set = true;
+    if (what == F64_POSITION || what == F64_VELOCITY) s->started = true;
+    g.primed = false;
+    return MIS_OK;
+}
+
+// engine state the getters read must describe the current frame: statics computed, fields evaluated at x
+static void ref64_refresh(MisSim* s, cudaStream_t st) {
+    RefEngine<double>& g = *R64(s);
+    ref_statics(g, st);
+    if (s->started && !(g.primed && !g.c.euler)) { ref_eval(g, g.s.x, g.s.fel, st); g.primed = !g.c.euler; }
+}
+
+extern "C" int mis_get_f64(MisSim* s, int what, double* dst_dev, void* stream) {
+    if (!s || !dst_dev) return fail(MIS_E_INVALID, "null argument");
+    if (!s->ref64) return fail(MIS_E_STATE, "mis_get_f64 needs a scene created with MisParams.fp64 = 1");
+    cudaStream_t st = (cudaStream_t)stream;
+    RefEngine<double>& g = *R64(s);
+    int dim = 0; bool stat = false;
+    double* src = f64_target(g, what, &dim, &stat);
+    if (!src) return fail(MIS_E_INVALID, "mis_get_f64: unknown `what`");
+    if (what >= F64_ELASTIC_FORCE) ref64_refresh(s, st);
+    ref::kr_scatter<double, double><<<nblk(s->n, 256), 256, 0, st>>>(src, s->perm, s->n, dim, dst_dev);
+    CK_LAUNCH(); s->launches++;
+    return MIS_OK;
+}
+
+// Reverse pass of the rollout (sim.py:341-372, compute_grad=True): loss value and d loss / d design x.
+extern "C" int mis_rollout_grad(MisSim* s, int frames, int n_targets, const float* target_x_dev, const float* target_v_dev,
+                                int checkpoint_every, double* loss_host, float* grad_dev, double* grad64_dev, void* stream) {
+    if (!s || frames <= 0 || n_targets < 0 || !loss_host || (n_targets > 0 && (!target_x_dev || !target_v_dev)))
+        return fail(MIS_E_INVALID, "mis_rollout_grad: bad argument");
+    if (!s->mass_set || !s->material_set) return fail(MIS_E_STATE, "set_mass and set_material must precede mis_rollout_grad");
+    if (s->p.euler) return fail(MIS_E_UNSUPPORTED, "mis_rollout_grad differentiates the velocity-Verlet loop of sim.py (not the Euler variant)");
+    if (s->sdf || s->halo_on) return fail(MIS_E_UNSUPPORTED, "mis_rollout_grad: obstacle contact and slab partitions are outside the differentiated path");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = s->n;
+    if (checkpoint_every <= 0) { checkpoint_every = 1; while (checkpoint_every * checkpoint_every < frames) checkpoint_every++; }
+    cudaError_t e;
+    if (s->ref64) {
+        RefEngine<double>& g = *R64(s);
+        e = ref_rollout_grad(g, s->v0, frames, n_targets, target_x_dev, target_v_dev, s->perm, checkpoint_every, loss_host, st);
+        CK(e);
+        ref::kr_design_grad<double><<<nblk(n, 256), 256, 0, st>>>(n, g.ratio_b, g.design, g.c.tanh_k, s->perm, grad_dev, grad64_dev);
+    } else {
+        if (!s->ref32) {
+            RefEngine<float>* g = new RefEngine<float>();
+            s->ref32 = g;
+            CK(ref_create(*g, n, s->nbr_start, s->nbr, s->p));
+        }
+        RefEngine<float>& g = *R32(s);
+        ref_pull(s, g, 63u, st);
+        e = ref_rollout_grad(g, s->v0, frames, n_targets, target_x_dev, target_v_dev, s->perm, checkpoint_every, loss_host, st);
+        CK(e);
+        ref::kr_design_grad<float><<<nblk(n, 256), 256, 0, st>>>(n, g.ratio_b, g.design, g.c.tanh_k, s->perm, grad_dev, grad64_dev);
+    }
+    CK_LAUNCH();
+    CK(cudaStreamSynchronize(st));
+    s->launches += 8LL * frames;
+    s->dirty = true; s->forces_only = false;
+    return MIS_OK;
+}
+
 extern "C" int mis_get_neighbor_info(MisSim* s, MisNeighborInfo* out) {
     if (!s || !out) return fail(MIS_E_INVALID, "null argument");
     out->total_pairs = s->total_pairs; out->max_neighbors = s->max_k; out->n = s->n;
@@ -560,22 +708,28 @@ extern "C" int mis_set_mass(MisSim* s, const float* mass_dev, void* stream) {
     CK_LAUNCH();
     s->launches += 3;
     s->mass_set = true; s->dirty = true; s->forces_only = false;
+    ref64_after_set(s, 2u, st);
     return MIS_OK;
 }
 
 extern "C" int mis_set_material(MisSim* s, const float* youngs_dev, const float* poisson_dev, void* stream) {
     if (!s || !youngs_dev || !poisson_dev) return fail(MIS_E_INVALID, "null argument");
     k_material<<<nblk(s->n, 256), 256, 0, (cudaStream_t)stream>>>(youngs_dev, poisson_dev, s->perm, s->n, s->matl);
-    CK_LAUNCH(); s->launches++;
+    ref::kr_gather<float, float><<<nblk(s->n, 256), 256, 0, (cudaStream_t)stream>>>(youngs_dev, s->perm, s->n, 1, s->raw_in);
+    ref::kr_gather<float, float><<<nblk(s->n, 256), 256, 0, (cudaStream_t)stream>>>(poisson_dev, s->perm, s->n, 1, s->raw_in + s->n);
+    CK_LAUNCH(); s->launches += 3;
     s->material_set = true; s->dirty = true; s->forces_only = false;
+    ref64_after_set(s, 4u, (cudaStream_t)stream);
     return MIS_OK;
 }
 
 extern "C" int mis_set_design(MisSim* s, const float* x_dev, void* stream) {
     if (!s || !x_dev) return fail(MIS_E_INVALID, "null argument");
     k_design<<<nblk(s->n, 256), 256, 0, (cudaStream_t)stream>>>(x_dev, s->perm, s->n, s->p.tanh_k, s->matl);
-    CK_LAUNCH(); s->launches++;
+    ref::kr_gather<float, float><<<nblk(s->n, 256), 256, 0, (cudaStream_t)stream>>>(x_dev, s->perm, s->n, 1, s->raw_in + 2 * (size_t)s->n);
+    CK_LAUNCH(); s->launches += 2;
     s->dirty = true; s->forces_only = false;
+    ref64_after_set(s, 8u, (cudaStream_t)stream);
     return MIS_OK;
 }
 
@@ -584,10 +738,12 @@ extern "C" int mis_set_ext_force(MisSim* s, const float* f_dev, void* stream) {
     k_gather_vec3<<<nblk(s->n, 256), 256, 0, (cudaStream_t)stream>>>(f_dev, s->perm, s->n, s->fext, 0);
     CK_LAUNCH(); s->launches++;
     if (!s->dirty) { s->dirty = true; s->forces_only = true; }
+    ref64_after_set(s, 16u, (cudaStream_t)stream);
     return MIS_OK;
 }
 
 extern "C" int mis_set_ext_force_host(MisSim* s, const float* f_host, void* stream) {
+    NO_FP64("host streaming");
     if (!s || !f_host) return fail(MIS_E_INVALID, "null argument");
     // upload on the copy stream (overlaps the kernels still running on `stream`), then gather on `stream`
     int rc = ensure_copy_stream(s);
@@ -609,6 +765,7 @@ extern "C" int mis_set_dirichlet(MisSim* s, const float* free_dev, void* stream)
     k_gather_vec3<<<nblk(s->n, 256), 256, 0, (cudaStream_t)stream>>>(free_dev, s->perm, s->n, s->freem, 0);
     CK_LAUNCH(); s->launches++;
     if (!s->dirty) { s->dirty = true; s->forces_only = true; }
+    ref64_after_set(s, 32u, (cudaStream_t)stream);
     return MIS_OK;
 }
 
@@ -710,7 +867,7 @@ static void enqueue_halo_sync(MisSim* s, cudaStream_t st) {
 // obstacle contact at the now-current positions: broad phase (bounding box) -> MLP values -> narrow phase (contact band)
 // -> three forward-difference evaluations of the particles in contact -> penalty force.  No host synchronisation:
 // the live row counts stay on the device and dead row-blocks of the GEMM grid exit at once.
-static cudaError_t enqueue_contact(MisSim* s, const View& v, cudaStream_t st) {
+static cudaError_t enqueue_contact(MisSim* s, const View& v, cudaStream_t st, cudaEvent_t after_layer0 = nullptr) {
     if (!s->sdf) return cudaSuccess;
     const int n = s->n, cap = s->con_cap;
     MisSdf* net = s->sdf;
@@ -720,7 +877,7 @@ static cudaError_t enqueue_contact(MisSim* s, const View& v, cudaStream_t st) {
     const long long l0 = net->launches;
     int fb = 0;
     const int H = net->H;
-    e = sdf_forward(net, s->con_pts, nullptr, cap, s->con_count, s->sdf_xf, make_float3(0.f, 0.f, 0.f), nullptr, st, 0, &fb);
+    e = sdf_forward(net, s->con_pts, nullptr, cap, s->con_count, s->sdf_xf, make_float3(0.f, 0.f, 0.f), nullptr, st, 0, &fb, false, after_layer0);
     if (e != cudaSuccess) return e;
     e = launch_k(k_contact_last_narrow, dim3(148 * 2), dim3(256), 0, st, true,
                  (const float*)net->act[fb][0], (const float*)net->act[fb][1], cap, (const int*)s->con_count, (const float*)net->wl, (const float*)net->bl, H, s->p.col_range,
@@ -745,8 +902,12 @@ static void enqueue_deform_contact(MisSim* s, const View& v, cudaStream_t st) {
     if (s->sdf && s->side_stream && !s->serial_contact) {
         cudaEventRecord(s->ev_fork, st);
         cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0);
-        e = enqueue_contact(s, v, s->side_stream);
+        // The chain's CTAs need ~200 KB of shared memory each (one per SM, 64 SMs); a deformation kernel that is already
+        // resident everywhere starves them until it drains.  Launched just behind the chain's first layer instead, the chain
+        // (higher-priority stream) takes its 64 SMs first and the deformation CTAs fill the other 84: the two overlap.
+        e = enqueue_contact(s, v, s->side_stream, s->contact_first ? s->ev_chain : nullptr);
         cudaEventRecord(s->ev_join, s->side_stream);
+        if (s->contact_first) cudaStreamWaitEvent(st, s->ev_chain, 0);
         enqueue_deform(s, v, st);
         cudaStreamWaitEvent(st, s->ev_join, 0);
     } else {
@@ -782,9 +943,23 @@ extern "C" int mis_startup(MisSim* s, const float v0[3], void* stream) {
     if (!s || !v0) return fail(MIS_E_INVALID, "null argument");
     cudaStream_t st = (cudaStream_t)stream;
     s->cur = 0;
+    s->v0[0] = v0[0]; s->v0[1] = v0[1]; s->v0[2] = v0[2];
     k_startup<<<nblk(s->n, 256), 256, 0, st>>>(s->x0m, s->n, make_float3(v0[0], v0[1], v0[2]), s->xv[0], s->vel);
+    if (s->ref64) ref_startup(*R64(s), s->v0, st);
     CK_LAUNCH(); s->launches++;
     s->started = true; s->dirty = true; s->forces_only = false;
+    return MIS_OK;
+}
+
+extern "C" int mis_startup_f64(MisSim* s, const double v0[3], void* stream) {
+    if (!s || !v0) return fail(MIS_E_INVALID, "null argument");
+    if (!s->ref64) return fail(MIS_E_STATE, "mis_startup_f64 needs a scene created with MisParams.fp64 = 1");
+    const float vf[3] = {(float)v0[0], (float)v0[1], (float)v0[2]};
+    int rc = mis_startup(s, vf, stream);
+    if (rc) return rc;
+    s->v0[0] = v0[0]; s->v0[1] = v0[1]; s->v0[2] = v0[2];
+    ref_startup(*R64(s), s->v0, (cudaStream_t)stream);
+    CK_LAUNCH();
     return MIS_OK;
 }
 
@@ -793,6 +968,11 @@ extern "C" int mis_set_state(MisSim* s, const float* x_dev, const float* v_dev, 
     cudaStream_t st = (cudaStream_t)stream;
     k_gather_vec3<<<nblk(s->n, 256), 256, 0, st>>>(x_dev, s->perm, s->n, s->xv[s->cur], 1);
     k_gather_vec3<<<nblk(s->n, 256), 256, 0, st>>>(v_dev, s->perm, s->n, s->vel, 0);
+    if (s->ref64) {
+        ref::kr_gather<double, float><<<nblk(s->n, 256), 256, 0, st>>>(x_dev, s->perm, s->n, 3, R64(s)->s.x);
+        ref::kr_gather<double, float><<<nblk(s->n, 256), 256, 0, st>>>(v_dev, s->perm, s->n, 3, R64(s)->s.v);
+        R64(s)->primed = false;
+    }
     CK_LAUNCH(); s->launches += 2;
     s->started = true; s->dirty = true; s->forces_only = false;
     return MIS_OK;
@@ -848,6 +1028,13 @@ extern "C" int mis_step(MisSim* s, int n_steps, void* stream) {
     if (!s || n_steps < 0) return fail(MIS_E_INVALID, "bad argument");
     if (!s->started) return fail(MIS_E_STATE, "mis_step before mis_startup / mis_set_state");
     cudaStream_t st = (cudaStream_t)stream;
+    if (s->ref64) {           // the whole scene steps in double (mis_ref.cuh); 8 launches per step
+        if (!s->mass_set || !s->material_set) return fail(MIS_E_STATE, "set_mass and set_material must precede startup/step");
+        for (int k = 0; k < n_steps; k++) ref_step(*R64(s), st);
+        s->launches += 8LL * n_steps;
+        CK_LAUNCH();
+        return MIS_OK;
+    }
     if (s->dirty) { int rc = prime(s, st); if (rc) return rc; }
     int chunk = s->p.graph_steps > 0 ? s->p.graph_steps : 32;
     int done = 0;
@@ -866,6 +1053,12 @@ extern "C" int mis_step(MisSim* s, int n_steps, void* stream) {
 extern "C" int mis_get_state(MisSim* s, float* x_dev, float* v_dev, void* stream) {
     if (!s) return fail(MIS_E_INVALID, "null sim");
     cudaStream_t st = (cudaStream_t)stream;
+    if (s->ref64) {           // rounded to fp32; mis_get_f64 returns the doubles
+        if (x_dev) ref::kr_scatter<double, float><<<nblk(s->n, 256), 256, 0, st>>>(R64(s)->s.x, s->perm, s->n, 3, x_dev);
+        if (v_dev) ref::kr_scatter<double, float><<<nblk(s->n, 256), 256, 0, st>>>(R64(s)->s.v, s->perm, s->n, 3, v_dev);
+        CK_LAUNCH(); s->launches += 2;
+        return MIS_OK;
+    }
     if (x_dev) { k_export_vec3<<<nblk(s->n, 256), 256, 0, st>>>(s->xv[s->cur], s->inv_perm, s->n, x_dev); s->launches++; }
     if (v_dev) { k_export_vec3<<<nblk(s->n, 256), 256, 0, st>>>(s->vel, s->inv_perm, s->n, v_dev); s->launches++; }
     CK_LAUNCH();
@@ -873,6 +1066,7 @@ extern "C" int mis_get_state(MisSim* s, float* x_dev, float* v_dev, void* stream
 }
 
 extern "C" int mis_get_state_host(MisSim* s, float* x_host, float* v_host, void* stream) {
+    NO_FP64("host streaming");
     if (!s) return fail(MIS_E_INVALID, "null sim");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t N3 = 3 * (size_t)s->n;
@@ -886,6 +1080,7 @@ extern "C" int mis_get_state_host(MisSim* s, float* x_host, float* v_host, void*
 // Streaming export: the un-permute kernels run on `stream`, the device->host copies on the library's copy stream, so the
 // next step's kernels overlap the transfer.  Two exports may be in flight (double-buffered staging).
 extern "C" int mis_get_state_host_async(MisSim* s, float* x_host, float* v_host, void* stream) {
+    NO_FP64("host streaming");
     if (!s || (!x_host && !v_host)) return fail(MIS_E_INVALID, "null argument");
     int rc = ensure_copy_stream(s);
     if (rc) return rc;
@@ -920,6 +1115,20 @@ extern "C" int mis_get_fields(MisSim* s, float* A_dev, float* R_dev, float* F_de
                               float* fel_dev, float* rho_dev, float* vol_dev, void* stream) {
     if (!s) return fail(MIS_E_INVALID, "null sim");
     cudaStream_t st = (cudaStream_t)stream;
+    if (s->ref64) {
+        RefEngine<double>& g = *R64(s);
+        ref64_refresh(s, st);
+        const int b = nblk(s->n, 256);
+        if (A_dev) ref::kr_scatter<double, float><<<b, 256, 0, st>>>(g.s.A, s->perm, s->n, 9, A_dev);
+        if (R_dev) ref::kr_scatter<double, float><<<b, 256, 0, st>>>(g.s.R, s->perm, s->n, 9, R_dev);
+        if (F_dev) ref::kr_scatter<double, float><<<b, 256, 0, st>>>(g.s.F, s->perm, s->n, 9, F_dev);
+        if (S_dev) ref::kr_scatter<double, float><<<b, 256, 0, st>>>(g.s.S, s->perm, s->n, 9, S_dev);
+        if (fel_dev) ref::kr_scatter<double, float><<<b, 256, 0, st>>>(g.s.fel, s->perm, s->n, 3, fel_dev);
+        if (rho_dev) ref::kr_scatter<double, float><<<b, 256, 0, st>>>(g.s.rho, s->perm, s->n, 1, rho_dev);
+        if (vol_dev) ref::kr_scatter<double, float><<<b, 256, 0, st>>>(g.s.vol, s->perm, s->n, 1, vol_dev);
+        CK_LAUNCH(); s->launches += 7;
+        return MIS_OK;
+    }
     if (s->started && s->dirty) { int rc = prime(s, st); if (rc) return rc; }
     View v = make_view(s);
     v.Apq = s->Apq;
@@ -940,6 +1149,16 @@ extern "C" int mis_eval_forces(MisSim* s, const float* x_dev, float* fel_dev, vo
     if (!s || !x_dev || !fel_dev) return fail(MIS_E_INVALID, "null argument");
     if (!s->mass_set || !s->material_set) return fail(MIS_E_STATE, "set_mass and set_material must precede mis_eval_forces");
     cudaStream_t st = (cudaStream_t)stream;
+    if (s->ref64) {
+        RefEngine<double>& g = *R64(s);
+        ref_statics(g, st);
+        ref::kr_gather<double, float><<<nblk(s->n, 256), 256, 0, st>>>(x_dev, s->perm, s->n, 3, g.s.xn);
+        ref_eval(g, g.s.xn, g.s.feln, st);
+        ref::kr_scatter<double, float><<<nblk(s->n, 256), 256, 0, st>>>(g.s.feln, s->perm, s->n, 3, fel_dev);
+        g.primed = false;                     // R, S, F now describe x_dev
+        CK_LAUNCH(); s->launches += 5;
+        return MIS_OK;
+    }
     // scratch position buffer carrying the volumes in .w
     CK(cudaMemcpyAsync(s->scratch4, s->xv[s->cur], (size_t)s->n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
     k_gather_vec3<<<nblk(s->n, 256), 256, 0, st>>>(x_dev, s->perm, s->n, s->scratch4, 1);
@@ -957,6 +1176,7 @@ extern "C" int mis_eval_forces(MisSim* s, const float* x_dev, float* fel_dev, vo
 
 // positions of frame f+1 (written by the fused part_1): xv[cur ^ 1] once the state is primed
 extern "C" int mis_gather_next_positions(MisSim* s, const int* ids_dev, int count, float* x_dev, void* stream) {
+    NO_FP64("halo plumbing");
     if (!s || count < 0 || (count > 0 && (!ids_dev || !x_dev))) return fail(MIS_E_INVALID, "bad argument");
     if (!s->started || s->dirty) return fail(MIS_E_STATE, "mis_gather_next_positions needs a primed state (mis_startup + mis_step)");
     if (s->p.euler) return fail(MIS_E_UNSUPPORTED, "halo plumbing supports the velocity-Verlet path only");
@@ -966,6 +1186,7 @@ extern "C" int mis_gather_next_positions(MisSim* s, const int* ids_dev, int coun
     return MIS_OK;
 }
 extern "C" int mis_scatter_next_positions(MisSim* s, const int* ids_dev, int count, const float* x_dev, void* stream) {
+    NO_FP64("halo plumbing");
     if (!s || count < 0 || (count > 0 && (!ids_dev || !x_dev))) return fail(MIS_E_INVALID, "bad argument");
     if (!s->started || s->dirty) return fail(MIS_E_STATE, "mis_scatter_next_positions needs a primed state (mis_startup + mis_step)");
     if (s->p.euler) return fail(MIS_E_UNSUPPORTED, "halo plumbing supports the velocity-Verlet path only");
@@ -976,6 +1197,7 @@ extern "C" int mis_scatter_next_positions(MisSim* s, const int* ids_dev, int cou
 }
 
 extern "C" int mis_set_volumes(MisSim* s, const int* ids_dev, int count, const float* vol_dev, void* stream) {
+    NO_FP64("halo plumbing");
     if (!s || count < 0 || (count > 0 && (!ids_dev || !vol_dev))) return fail(MIS_E_INVALID, "bad argument");
     if (!s->mass_set) return fail(MIS_E_STATE, "mis_set_volumes before mis_set_mass");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1048,6 +1270,7 @@ extern "C" int mis_ipc_close(void* dev_ptr) {
 extern "C" int mis_halo_connect(MisSim* s, int n_peers, void* const* peer_xv0, void* const* peer_xv1, void* const* peer_flag,
                                 int n_push, const int* push_ids_dev, const int* push_peer_dev, const int* push_slot_dev,
                                 int n_ghost, const int* ghost_ids_dev, const int* ghost_layer_dev, void* stream) {
+    NO_FP64("halo plumbing");
     if (!s || n_peers < 0 || n_peers > MIS_MAX_PEERS || n_push < 0 || n_ghost < 0) return fail(MIS_E_INVALID, "mis_halo_connect: bad argument");
     if (n_peers > 0 && (!peer_xv0 || !peer_xv1 || !peer_flag)) return fail(MIS_E_INVALID, "mis_halo_connect: null peer table");
     if (n_push > 0 && (!push_ids_dev || !push_peer_dev || !push_slot_dev)) return fail(MIS_E_INVALID, "mis_halo_connect: null push list");
@@ -1108,6 +1331,7 @@ extern "C" int mis_halo_status(MisSim* s, void* stream, int* err, long long* exc
 }
 
 extern "C" int mis_accumulate_loss(MisSim* s, const float* target_x_dev, const float* target_v_dev, double* loss_dev, void* stream) {
+    NO_FP64("mis_accumulate_loss (use mis_rollout_grad)");
     if (!s || !target_x_dev || !target_v_dev || !loss_dev) return fail(MIS_E_INVALID, "null argument");
     if (!s->started) return fail(MIS_E_STATE, "mis_accumulate_loss before mis_startup / mis_set_state");
     cudaStream_t st = (cudaStream_t)stream;
@@ -1145,6 +1369,7 @@ extern "C" long long mis_launch_count(MisSim* s) { return s ? s->launches : 0; }
 // n_steps steps launched one kernel at a time with a CUDA event pair around each launch on
 // `stream`; returns the summed device time per kernel family.  Synchronises the host.
 extern "C" int mis_profile_step(MisSim* s, int n_steps, void* stream, double* ms_deform, double* ms_force) {
+    NO_FP64("mis_profile_step");
     if (!s || n_steps <= 0) return fail(MIS_E_INVALID, "bad argument");
     if (!s->started) return fail(MIS_E_STATE, "mis_profile_step before mis_startup / mis_set_state");
     if (s->sdf) return fail(MIS_E_UNSUPPORTED, "mis_profile_step times the two gather kernels alone: remove the obstacle first (mis_set_sdf_contact(sim, NULL, ...))");
@@ -1313,6 +1538,7 @@ extern "C" int mis_sdf_profile_gemm(MisSdf* s, int m, int reps, void* stream, do
 }
 
 extern "C" int mis_set_sdf_contact(MisSim* s, MisSdf* sdf, const float* xform_host, const float* bbox_host, float fd_eps, void* stream) {
+    NO_FP64("obstacle contact");
     if (!s) return fail(MIS_E_INVALID, "null sim");
     drop_graph(s);
     s->dirty = true; s->forces_only = false;
@@ -1329,8 +1555,11 @@ extern "C" int mis_set_sdf_contact(MisSim* s, MisSdf* sdf, const float* xform_ho
         CK(cudaStreamCreateWithPriority(&s->side_stream, cudaStreamNonBlocking, hi));
         CK(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s->ev_chain, cudaEventDisableTiming));
         const char* e = getenv("MIS_SERIAL_CONTACT");
         s->serial_contact = e && e[0] == '1';
+        const char* f = getenv("MIS_CONTACT_FIRST");
+        s->contact_first = !(f && f[0] == '0');
     }
     CK(cudaMemsetAsync(s->con_count, 0, 4 * sizeof(int), (cudaStream_t)stream));
     {   // rows one pass of the chain can take: the activations are 16 KB per row (4 buffers x H floats), so the capacity is bounded

@@ -97,7 +97,8 @@ inline cudaError_t sdf_reserve(MisSdf* s, int rows) {
 // (the caller runs its own fused last-layer kernel).
 // pdl_first: layer 0 is a programmatic dependent launch of the caller's previous kernel (which must call pdl_trigger / exit).
 inline cudaError_t sdf_forward(MisSdf* s, const float* pts, const int* idx, int rows, const int* m_count, const SdfXform& xf, float3 shift,
-                               float* out, cudaStream_t st, int fd3 = 0, int* final_buf = nullptr, bool pdl_first = false) {
+                               float* out, cudaStream_t st, int fd3 = 0, int* final_buf = nullptr, bool pdl_first = false,
+                               cudaEvent_t after_layer0 = nullptr) {
     static bool attr_set_dev[64] = {};                 // the opt-in shared-memory size is a per-DEVICE function attribute
     int dev_ = 0;
     cudaGetDevice(&dev_);
@@ -119,6 +120,7 @@ inline cudaError_t sdf_forward(MisSdf* s, const float* pts, const int* idx, int 
                               pts, idx, rows, m_pad, m_count, xf, shift, fd3, (const float*)s->W0, (const float*)s->b0, H, s->act[0][0], s->act[0][1]);
     if (le != cudaSuccess) return le;
     s->launches++;
+    if (after_layer0) cudaEventRecord(after_layer0, st);            // the GEMM chain is the next launch on this stream
     // few rows (a device-side count = the per-step contact query, or a small host-side count): split-K over 8-CTA clusters;
     // bulk queries: persistent 128 x 256 tiles
     const bool skinny = s->force_path ? (s->force_path == 1 || s->force_path == 3) : (H <= SK_MAX_KBS * SK_SPLIT * SDF_BK && (m_count != nullptr || rows <= 1024));

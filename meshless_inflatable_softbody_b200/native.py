@@ -14,7 +14,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.environ.get("MIS_LIB") or os.path.join(_PKG, "libmis_b200.so")   # MIS_LIB: tuning builds only
 SOURCES = ["mis_api.cu"]
-HEADERS = ["mis_math.cuh", "mis_sort.cuh", "mis_neighbors.cuh", "mis_cluster.cuh", "mis_tile.cuh", "mis_sdf.cuh", "mis_sdf_host.cuh"]
+HEADERS = ["mis_math.cuh", "mis_sort.cuh", "mis_neighbors.cuh", "mis_cluster.cuh", "mis_tile.cuh", "mis_ref.cuh", "mis_ref_host.cuh", "mis_sdf.cuh", "mis_sdf_host.cuh"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -29,7 +29,7 @@ class MisParams(C.Structure):
         ("symmetric_pair", C.c_int), ("identity_rot", C.c_int), ("self_density", C.c_int),
         ("euler", C.c_int), ("no_contact", C.c_int),
         ("lanes_per_particle", C.c_int), ("keep_fields", C.c_int), ("graph_steps", C.c_int),
-        ("two_pass_deform", C.c_int), ("cluster_size", C.c_int),
+        ("two_pass_deform", C.c_int), ("cluster_size", C.c_int), ("fp64", C.c_int),
     ]
 
 
@@ -109,6 +109,11 @@ SYMBOLS = {
     "mis_accumulate_loss": (C.c_int, [_vp, _fp, _fp, _vp, _vp]),
     "mis_set_gather_mode": (C.c_int, [_vp, C.c_int, _vp]),
     "mis_get_gather_info": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "mis_set_f64": (C.c_int, [_vp, C.c_int, _fp, _vp]),
+    "mis_get_f64": (C.c_int, [_vp, C.c_int, _fp, _vp]),
+    "mis_set_constants_f64": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "mis_startup_f64": (C.c_int, [_vp, C.POINTER(C.c_double), _vp]),
+    "mis_rollout_grad": (C.c_int, [_vp, C.c_int, C.c_int, _fp, _fp, C.c_int, C.POINTER(C.c_double), _fp, _fp, _vp]),
     "mis_launch_count": (C.c_longlong, [_vp]),
     "mis_profile_step": (C.c_int, [_vp, C.c_int, _vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "mis_gather_next_positions": (C.c_int, [_vp, _ip, C.c_int, _fp, _vp]),

@@ -30,13 +30,17 @@ class Simulator:
     def __init__(self, x0, config: Optional[SceneConfig] = None, device: str = "cuda:0",
                  lanes_per_particle: int = 0, keep_fields: bool = False, graph_steps: int = 0,
                  two_pass_deform: bool = False, cluster_size: int = 0,
-                 apply_defaults: bool = True):
+                 apply_defaults: bool = True, precision: str = "f32"):
         if not torch.cuda.is_available():
             raise RuntimeError("meshless_inflatable_softbody_b200.Simulator needs a CUDA device (sm_100a); "
                                "there is no CPU fallback")
         self.cfg = config or SceneConfig()
         self.device = torch.device(device)
         self.L = native.lib()
+        if precision not in ("f32", "f64"):
+            raise ValueError("precision must be 'f32' (sim.py, real = wp.float32) or 'f64' (sim_taichi.py, real = ti.f64)")
+        self.f64 = precision == "f64"
+        x0_64 = np.ascontiguousarray(np.asarray(x0, dtype=np.float64).reshape(-1, 3)) if self.f64 else None
         x0_np = np.ascontiguousarray(np.asarray(x0, dtype=np.float32).reshape(-1, 3))
         self.n = int(x0_np.shape[0])
         self.x0 = torch.from_numpy(x0_np).to(self.device)
@@ -52,6 +56,7 @@ class Simulator:
         p.lanes_per_particle, p.keep_fields, p.graph_steps = int(lanes_per_particle), int(keep_fields), int(graph_steps)
         p.two_pass_deform = int(two_pass_deform)
         p.cluster_size = int(cluster_size)
+        p.fp64 = int(self.f64)
         self.params = p
         self.hash_grid = (gx, gy, gz)
         with torch.cuda.device(self.device):
@@ -60,6 +65,10 @@ class Simulator:
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
         native.check(self.L.mis_create(self.n, self.x0.data_ptr(), C.byref(p), self._st(), C.byref(self._h)), "mis_create")
         self.frame = 0
+        if self.f64:            # the neighbour structure was binned on the fp32 rounding of x0; the state and the constants are doubles
+            self._set64(0, x0_64, 3)
+            k = (C.c_double * 8)(c.h, c.damping, c.time_step, c.collision_penalty_stiffness, c.collision_range, c.stiffness_a, c.stiffness_b, c.tanh_k)
+            native.check(self.L.mis_set_constants_f64(self._h, k), "mis_set_constants_f64")
         if apply_defaults:      # main(), sim.py:441-444 + x.fill_(-1.), sim.py:99
             self.set_all_external_force(c.external_force)
             self.set_youngs_modulus(c.youngs_modulus)
@@ -95,6 +104,27 @@ class Simulator:
             if t is not None and t.is_cuda:
                 t.record_stream(self.stream)
 
+    # fp64 scenes: doubles in and out (include/mis.h: mis_set_f64 / mis_get_f64)
+    _F64 = {"x0": 0, "mass": 1, "youngs": 2, "poisson": 3, "design": 4, "fext": 5, "free": 6, "x": 7, "v": 8, "fel": 9, "vol": 10,
+            "rho": 11, "F": 12, "S": 13, "R": 14, "A": 15}
+
+    def _set64(self, what: int, a, dim: int):
+        if isinstance(a, torch.Tensor):
+            t = a.to(device=self.device, dtype=torch.float64)
+        else:
+            t = torch.as_tensor(np.asarray(a, dtype=np.float64), device=self.device)
+        t = t.expand((self.n, dim) if dim > 1 else (self.n,)).contiguous()
+        self._publish(t)
+        native.check(self.L.mis_set_f64(self._h, int(what), t.data_ptr(), self._st()), "mis_set_f64")
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+    def _get64(self, what: int, dim) -> torch.Tensor:
+        shape = (self.n,) if dim == 1 else ((self.n, 3) if dim == 3 else (self.n, 3, 3))
+        out = torch.empty(shape, device=self.device, dtype=torch.float64)
+        native.check(self.L.mis_get_f64(self._h, int(what), out.data_ptr(), self._st()), "mis_get_f64")
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        return out
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             self.synchronize()
@@ -112,16 +142,24 @@ class Simulator:
 
     # ------------------------------------------------------------------ control functions (sim.py:279-308)
     def set_all_external_force(self, f: Sequence[float]):
+        if self.f64:
+            return self._set64(5, f, 3)
         self._fext = self._dev(f, (self.n, 3), own=True)
         native.check(self.L.mis_set_ext_force(self._h, self._fext.data_ptr(), self._st()), "mis_set_ext_force")
 
     def set_external_force(self, i, f):
         """sim.py:279-280; i may be an index or an index array."""
+        if self.f64:
+            cur = self._get64(5, 3)
+            cur[i] = torch.as_tensor(np.asarray(f, np.float64), device=self.device)
+            return self._set64(5, cur, 3)
         self._fext[i] = torch.as_tensor(np.asarray(f, np.float32), device=self.device)
         self._publish(self._fext)
         native.check(self.L.mis_set_ext_force(self._h, self._fext.data_ptr(), self._st()), "mis_set_ext_force")
 
     def set_external_forces(self, f):
+        if self.f64:
+            return self._set64(5, f, 3)
         self._fext = self._dev(f, (self.n, 3), own=True)
         native.check(self.L.mis_set_ext_force(self._h, self._fext.data_ptr(), self._st()), "mis_set_ext_force")
 
@@ -131,6 +169,10 @@ class Simulator:
 
     def set_dirichlet(self, i, d):
         """sim.py:285-286: free_points[i] = d (component-wise multiplier)."""
+        if self.f64:
+            cur = self._get64(6, 3)
+            cur[i] = torch.as_tensor(np.asarray(d, np.float64), device=self.device)
+            return self._set64(6, cur, 3)
         if not hasattr(self, "_free"):
             self._free = torch.ones((self.n, 3), device=self.device, dtype=torch.float32)
         self._free[i] = torch.as_tensor(np.asarray(d, np.float32), device=self.device)
@@ -138,31 +180,53 @@ class Simulator:
         native.check(self.L.mis_set_dirichlet(self._h, self._free.data_ptr(), self._st()), "mis_set_dirichlet")
 
     def set_youngs_modulus(self, E):
+        if self.f64:
+            self._set64(2, E, 1)
+            if not hasattr(self, "_nu64"):
+                self._set64(3, 0.0, 1)        # sim_taichi.py:259-264 reads poisson_ratio before it is set: zero-initialised field
+            self._E64 = True
+            return
         self._E = self._dev(E, (self.n,), own=True)
         if hasattr(self, "_nu"):
             native.check(self.L.mis_set_material(self._h, self._E.data_ptr(), self._nu.data_ptr(), self._st()), "mis_set_material")
 
     def set_poisson_ratio(self, nu):
+        if self.f64:
+            self._nu64 = True
+            return self._set64(3, nu, 1)
         self._nu = self._dev(nu, (self.n,), own=True)
         if hasattr(self, "_E"):
             native.check(self.L.mis_set_material(self._h, self._E.data_ptr(), self._nu.data_ptr(), self._st()), "mis_set_material")
 
     def set_mass(self, m):
+        if self.f64:
+            return self._set64(1, m, 1)
         self._m = self._dev(m, (self.n,), own=True)
         native.check(self.L.mis_set_mass(self._h, self._m.data_ptr(), self._st()), "mis_set_mass")
 
     def set_design(self, x):
         """x -> ratio = 0.5 tanh(k x) + 0.5 (compute_ratio, sim.py:107-110)."""
+        if self.f64:
+            return self._set64(4, x, 1)
         self._x = self._dev(x, (self.n,), own=True)
         native.check(self.L.mis_set_design(self._h, self._x.data_ptr(), self._st()), "mis_set_design")
 
     # ------------------------------------------------------------------ rollout (sim.py:341-358)
     def startup(self, v0: Optional[Sequence[float]] = None):
-        v = (C.c_float * 3)(*(v0 if v0 is not None else self.cfg.initial_velocity))
+        self._v0 = tuple(v0) if v0 is not None else tuple(self.cfg.initial_velocity)
+        if self.f64:
+            native.check(self.L.mis_startup_f64(self._h, (C.c_double * 3)(*self._v0), self._st()), "mis_startup_f64")
+            self.frame = 0
+            return
+        v = (C.c_float * 3)(*self._v0)
         native.check(self.L.mis_startup(self._h, v, self._st()), "mis_startup")
         self.frame = 0
 
     def set_state(self, x, v, frame: int = 0):
+        if self.f64:
+            self._set64(7, x, 3); self._set64(8, v, 3)
+            self.frame = frame
+            return
         xd, vd = self._dev(x, (self.n, 3)), self._dev(v, (self.n, 3))
         native.check(self.L.mis_set_state(self._h, xd.data_ptr(), vd.data_ptr(), self._st()), "mis_set_state")
         self.stream.synchronize()
@@ -285,6 +349,8 @@ class Simulator:
 
     # ------------------------------------------------------------------ state export
     def position_velocity(self):
+        if self.f64:
+            return self._get64(7, 3), self._get64(8, 3)
         x = torch.empty((self.n, 3), device=self.device, dtype=torch.float32)
         v = torch.empty((self.n, 3), device=self.device, dtype=torch.float32)
         native.check(self.L.mis_get_state(self._h, x.data_ptr(), v.data_ptr(), self._st()), "mis_get_state")
@@ -313,6 +379,9 @@ class Simulator:
         native.check(self.L.mis_wait_state_host(self._h, int(pending_allowed)), "mis_wait_state_host")
 
     def fields(self, want=("R", "F", "S", "fel", "rho", "vol")):
+        if self.f64:
+            dims = {"A": 9, "R": 9, "F": 9, "S": 9, "fel": 3, "rho": 1, "vol": 1}
+            return {k: self._get64(self._F64[k], dims[k]) for k in want}
         out = {}
         shapes = {"A": (self.n, 3, 3), "R": (self.n, 3, 3), "F": (self.n, 3, 3), "S": (self.n, 3, 3),
                   "fel": (self.n, 3), "rho": (self.n,), "vol": (self.n,)}
@@ -359,6 +428,35 @@ class Simulator:
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
         native.check(self.L.mis_accumulate_loss(self._h, tx.data_ptr(), tv.data_ptr(), loss.data_ptr(), self._st()), "mis_accumulate_loss")
         torch.cuda.current_stream(self.device).wait_stream(self.stream)     # keeps tx / tv alive until the kernel has read them
+
+    def rollout_grad(self, targets, frames: Optional[int] = None, checkpoint_every: int = 0):
+        """diff_sim(compute_grad=True) (sim.py:341-372): (loss, d loss / d design x).  targets: a folder of position_{i}.npy /
+        velocity_{i}.npy (sim.py:118-119) or a list of (x, v) arrays; target i is compared at frame (frames // len(targets)) * (i + 1).
+        The reverse pass (wp.Tape.backward in the reference) is the hand-written adjoint of mis_ref.cuh with checkpointed
+        recomputation instead of 3 001 stored frames.  The gradient is float64 for fp64 scenes, float32 otherwise."""
+        if isinstance(targets, (str, os.PathLike)):
+            k, pairs = 1, []
+            while os.path.exists(os.path.join(targets, f"position_{k}.npy")):
+                pairs.append((np.load(os.path.join(targets, f"position_{k}.npy")), np.load(os.path.join(targets, f"velocity_{k}.npy"))))
+                k += 1
+            targets = pairs
+        frames = frames or self.cfg.frames
+        nt = len(targets)
+        tx = torch.as_tensor(np.stack([np.asarray(t[0], np.float32).reshape(self.n, 3) for t in targets]) if nt else np.zeros((1, self.n, 3), np.float32),
+                             device=self.device).contiguous()
+        tv = torch.as_tensor(np.stack([np.asarray(t[1], np.float32).reshape(self.n, 3) for t in targets]) if nt else np.zeros((1, self.n, 3), np.float32),
+                             device=self.device).contiguous()
+        self._publish(tx, tv)
+        loss = C.c_double(0.0)
+        g32 = None if self.f64 else torch.zeros(self.n, device=self.device, dtype=torch.float32)
+        g64 = torch.zeros(self.n, device=self.device, dtype=torch.float64) if self.f64 else None
+        self.startup(getattr(self, "_v0", None))
+        native.check(self.L.mis_rollout_grad(self._h, int(frames), int(nt), tx.data_ptr(), tv.data_ptr(), int(checkpoint_every), C.byref(loss),
+                                             g32.data_ptr() if g32 is not None else None, g64.data_ptr() if g64 is not None else None, self._st()),
+                     "mis_rollout_grad")
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        self.frame = 0
+        return float(loss.value), (g64 if self.f64 else g32)
 
     def rollout_loss(self, targets, frames: Optional[int] = None) -> float:
         """Forward value of the reference's objective (diff_sim without the tape, sim.py:341-362): startup, `frames` steps, and

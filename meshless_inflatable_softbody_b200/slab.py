@@ -58,10 +58,15 @@ class SlabPartition:
     plans: List[RankPlan]
 
     @classmethod
-    def build(cls, x0: np.ndarray, h: float, world_size: int, axis: Optional[int] = None, ghost_layers: int = 2) -> "SlabPartition":
+    def build(cls, x0: np.ndarray, h: float, world_size: int, axis: Optional[int] = None, ghost_layers: int = 2,
+              extra_cost: Optional[np.ndarray] = None) -> "SlabPartition":
         """Cut planes at quantiles of the x0 coordinate along `axis` (equal owned counts, to the particle); ghost layer L of a
         rank = foreign particles within L * 2h of its slab along the axis.  Every neighbour (|x0_i - x0_j| < 2h, sim.py:137-141)
-        of an owned particle is owned or layer 1; every neighbour of a layer-1 ghost is local."""
+        of an owned particle is owned or layer 1; every neighbour of a layer-1 ghost is local.
+
+        extra_cost[r]: fixed per-step work of rank r that is not proportional to its particle count (e.g. the obstacle's MLP
+        query, which only the ranks under the obstacle run), in particle-equivalents: the cuts then equalise
+        owned_r + extra_cost[r] instead of owned_r.  The partition is static, so this is a one-off load balance."""
         x0 = np.asarray(x0, np.float32).reshape(-1, 3)
         n = len(x0)
         if axis is None:
@@ -70,9 +75,14 @@ class SlabPartition:
         order = np.argsort(c, kind="stable")
         cs = c[order]
         reach = 2.0 * float(np.float32(h)) * (1.0 + 1e-4)          # support radius plus a margin far above fp32 rounding of the distance test
+        extra = np.zeros(world_size) if extra_cost is None else np.asarray(extra_cost, np.float64).reshape(world_size)
+        share = (n + extra.sum()) / world_size                       # cost every rank should carry
+        owned_target = np.maximum(share - extra, 0.0)
+        owned_target *= n / owned_target.sum()
+        bounds = np.concatenate([[0.0], np.cumsum(owned_target)])
         cuts = [-np.inf]
         for r in range(1, world_size):
-            k = int(round(r * n / world_size))
+            k = int(round(bounds[r]))
             k = min(max(k, 1), n - 1)
             cuts.append(0.5 * (cs[k - 1] + cs[k]) if cs[k] > cs[k - 1] else cs[k])
         cuts.append(np.inf)
@@ -231,7 +241,7 @@ class SlabSimulator:
 
     def __init__(self, x0_global, config=None, rank: int = 0, world_size: int = 1, device: str = "cuda:0",
                  group=None, partition: Optional[SlabPartition] = None, in_process: bool = False, halo: str = "auto",
-                 **sim_kw):
+                 extra_cost=None, **sim_kw):
         import torch
         import torch.distributed as dist
         from .config import SceneConfig
@@ -242,7 +252,7 @@ class SlabSimulator:
         self.dist, self.group = dist, group
         x0_global = np.asarray(x0_global, np.float32).reshape(-1, 3)
         self.n_global = len(x0_global)
-        self.partition = partition or SlabPartition.build(x0_global, self.cfg.h, world_size)
+        self.partition = partition or SlabPartition.build(x0_global, self.cfg.h, world_size, extra_cost=extra_cost)
         self.plan = self.partition.plans[rank]
         self.device = torch.device(device)
         local = self.plan.local_ids

@@ -6,6 +6,7 @@
 #include "mis_sort.cuh"
 #include "mis_cluster.cuh"
 #include "mis_tile.cuh"
+#include "mis_tilebuild.cuh"
 #include "mis_sdf_host.cuh"
 
 #include <math.h>
@@ -80,6 +81,8 @@ struct MisSim {
         unsigned short* lists = nullptr; long long lists_cap = 0, total_blocks = 0;
         float4* AB = nullptr;
         int* max_dev = nullptr;
+        uint32_t* bits = nullptr; long long bits_cap = 0; int W = 0;       // neighbour bitmasks over the tile (mis_tilebuild.cuh)
+        bool tab_ok = false;                                               // the tile table of the current binning exists
     } tile;
     // cell-sorted state
     float4 *x0m = nullptr, *xv[2] = {nullptr, nullptr}, *vel = nullptr, *f1 = nullptr, *fel = nullptr;
@@ -158,6 +161,7 @@ template <typename T>
 static cudaError_t dalloc(T** p, size_t count) { return cudaMalloc((void**)p, count * sizeof(T) + 64); }
 
 static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e && e[0] ? atoi(e) : dflt; }
 
 extern "C" const char* mis_last_error(void) { return g_err.c_str(); }
 extern "C" const char* mis_version(void) { return "mis_b200 sm_100a (" __DATE__ ")"; }
@@ -306,7 +310,7 @@ extern "C" int mis_destroy(MisSim* s) {
     if (s->ref32) { R32(s)->release(); delete R32(s); }
     if (s->ref64) { R64(s)->release(); delete R64(s); }
     if (s->raw_in) cudaFree(s->raw_in);
-    void* tptrs[] = {s->tile.wkey, s->tile.order, s->tile.tab, s->tile.flag, s->tile.pos, s->tile.nblocks, s->tile.blk_start, s->tile.t_off, s->tile.lists, s->tile.AB, s->tile.max_dev};
+    void* tptrs[] = {s->tile.bits, s->tile.wkey, s->tile.order, s->tile.tab, s->tile.flag, s->tile.pos, s->tile.nblocks, s->tile.blk_start, s->tile.t_off, s->tile.lists, s->tile.AB, s->tile.max_dev};
     for (void* p : tptrs) if (p) cudaFree(p);
     delete s;
     return MIS_OK;
@@ -358,10 +362,11 @@ template <int CAP, int MINB> static cudaError_t tile_attr_d() {
 template <int CAP> static cudaError_t tile_attr_f() {
     return cudaFuncSetAttribute(k_force_t<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, tile_smem_force<CAP>());
 }
-static int build_tiles(MisSim* s, cudaStream_t st) {
+// active-cell table of the current binning: flag / scan / one row per non-empty cell; largest tile and cell
+static int build_tile_tab(MisSim* s, cudaStream_t st) {
     MisSim::Tile& t = s->tile;
     const int n = s->n;
-    t.ok = false;
+    t.ok = false; t.tab_ok = false;
     if (!t.flag) {
         CK(dalloc(&t.flag, (size_t)n)); CK(dalloc(&t.pos, (size_t)n + 1)); CK(dalloc(&t.nblocks, (size_t)n));
         CK(dalloc(&t.blk_start, (size_t)n + 1)); CK(dalloc(&t.t_off, (size_t)n)); CK(dalloc(&t.AB, 5 * (size_t)n)); CK(dalloc(&t.max_dev, 2));
@@ -382,34 +387,45 @@ static int build_tiles(MisSim* s, cudaStream_t st) {
         CK(dalloc(&t.tab, (size_t)t.n_active * TT_STRIDE));
         t.tab_cap = t.n_active;
     }
-    k_tile_tab<<<nblk((long long)n * 32, 256), 256, 0, st>>>(t.flag, t.pos, s->cell_lin_sorted, s->cell_start, s->cell_end, cdim, n, t.tab, t.max_dev,
-                                                            s->nbr_start, t.wkey, t.order);
+    k_tile_tab<<<nblk((long long)n * 32, 256), 256, 0, st>>>(t.flag, t.pos, s->cell_lin_sorted, s->cell_start, s->cell_end, cdim, n, t.tab, t.max_dev);
     CK_LAUNCH(); s->launches++;
-    s->launches += radix_sort_pairs(t.wkey, t.order, t.n_active, 20, s->rs, st);      // longest cell first
-    CK_LAUNCH();
-    k_tile_count<<<nblk(n, 256), 256, 0, st>>>(s->nbr_count, n, t.nblocks);
-    CK_LAUNCH(); s->launches++;
-    s->launches += exclusive_scan<unsigned long long>(t.nblocks, t.blk_start, n, s->scan_tmp, st);
     int mx[2] = {0, 0};
-    unsigned long long tb = 0;
     CK(cudaMemcpyAsync(mx, t.max_dev, sizeof mx, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&tb, t.blk_start + n, sizeof tb, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    t.max_tile = mx[0]; t.max_own = mx[1]; t.total_blocks = (long long)tb;
+    t.max_tile = mx[0]; t.max_own = mx[1];
     t.cap_d = t.cap_f = 0;
     for (int c : TILE_CAPS_D) if (!t.cap_d && t.max_tile <= c) t.cap_d = c;
     for (int c : TILE_CAPS_F) if (!t.cap_f && t.max_tile <= c) t.cap_f = c;
-    if (!t.cap_d || !t.cap_f) return MIS_OK;          // a neighbourhood too dense for one tile: the cluster kernels run instead
+    t.W = (t.max_tile + 31) / 32;
+    t.tab_ok = true;
+    return MIS_OK;
+}
+// list blocks per particle -> offsets; allocates the uint16 lists.  Needs nbr_count.  One host round trip.
+static int alloc_tile_lists(MisSim* s, cudaStream_t st) {
+    MisSim::Tile& t = s->tile;
+    const int n = s->n;
+    k_tile_count<<<nblk(n, 256), 256, 0, st>>>(s->nbr_count, n, t.nblocks);
+    CK_LAUNCH(); s->launches++;
+    s->launches += exclusive_scan<unsigned long long>(t.nblocks, t.blk_start, n, s->scan_tmp, st);
+    unsigned long long tb = 0;
+    CK(cudaMemcpyAsync(&tb, t.blk_start + n, sizeof tb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    t.total_blocks = (long long)tb;
     if (t.total_blocks > t.lists_cap || !t.lists) {
         if (t.lists) cudaFree(t.lists);
         t.lists = nullptr;
         CK(dalloc(&t.lists, (size_t)(t.total_blocks + 1) * TILE_BLOCK));
         t.lists_cap = t.total_blocks;
     }
-    k_tile_lists<<<nblk((long long)n * 32, 256), 256, 0, st>>>(s->nbr_start, s->nbr, s->nbr_count, s->cell_lin_sorted, s->cell_start, t.pos, t.tab, cdim, n,
-                                                              t.blk_start, t.t_off, t.lists);
+    return MIS_OK;
+}
+// launch order (longest cell first) and the per-device function attributes of the instantiations this scene uses
+static int finish_tiles(MisSim* s, cudaStream_t st) {
+    MisSim::Tile& t = s->tile;
+    k_tile_work<<<nblk(t.n_active, 256), 256, 0, st>>>(t.tab, t.n_active, s->nbr_start, t.wkey, t.order);
     CK_LAUNCH(); s->launches++;
-    // per device: the opt-in shared-memory size of the instantiations this scene uses
+    s->launches += radix_sort_pairs(t.wkey, t.order, t.n_active, 20, s->rs, st);
+    CK_LAUNCH();
     cudaError_t e = cudaSuccess;
     switch (t.cap_d) {
         case 2048: e = tile_attr_d<2048, 3>(); break; case 2560: e = tile_attr_d<2560, 2>(); break;
@@ -419,6 +435,84 @@ static int build_tiles(MisSim* s, cudaStream_t st) {
     switch (t.cap_f) { case 2048: e = tile_attr_f<2048>(); break; case 2560: e = tile_attr_f<2560>(); break; default: e = tile_attr_f<2816>(); break; }
     CK(e);
     t.ok = true;
+    return MIS_OK;
+}
+// uint16 tile lists from exact lists that the per-thread walk built (scenes whose tiles exceed the bitmask build)
+static int build_tiles(MisSim* s, cudaStream_t st) {
+    MisSim::Tile& t = s->tile;
+    if (t.ok) return MIS_OK;
+    if (!t.tab_ok) { int rc = build_tile_tab(s, st); if (rc) return rc; }
+    if (!t.cap_d || !t.cap_f) return MIS_OK;          // a neighbourhood too dense for one tile: the cluster kernels run instead
+    int rc = alloc_tile_lists(s, st);
+    if (rc) return rc;
+    const int3 cdim = make_int3(s->cell_dim[0], s->cell_dim[1], s->cell_dim[2]);
+    k_tile_lists<<<nblk((long long)s->n * 32, 256), 256, 0, st>>>(s->nbr_start, s->nbr, s->nbr_count, s->cell_lin_sorted, s->cell_start, t.pos, t.tab, cdim, s->n,
+                                                                 t.blk_start, t.t_off, t.lists);
+    CK_LAUNCH(); s->launches++;
+    return finish_tiles(s, st);
+}
+// Exact lists, uint16 tile lists and (clusters of 2) union lists from ONE pass of distance tests over shared-memory tiles.
+static int build_lists_tiled(MisSim* s, cudaStream_t st) {
+    MisSim::Tile& t = s->tile;
+    const int n = s->n, W = t.W;
+    const int3 cdim = make_int3(s->cell_dim[0], s->cell_dim[1], s->cell_dim[2]);
+    if ((long long)n * W > t.bits_cap) {
+        if (t.bits) cudaFree(t.bits);
+        t.bits = nullptr;
+        CK(dalloc(&t.bits, (size_t)n * W));
+        t.bits_cap = (long long)n * W;
+    }
+    const bool pairs = s->C == 2 && !s->merge_lists;
+    const int smem = tb_smem_bytes(W, t.max_own);
+    CK(cudaFuncSetAttribute(k_tile_walk_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CK(cudaMemsetAsync(s->max_k_dev, 0, sizeof(int), st));
+    k_tile_walk_bits<<<t.n_active, TB_THREADS, smem, st>>>(nullptr, t.tab, s->x0m, n, s->d2_limit, W, t.max_own, t.bits, s->nbr_count, s->max_k_dev,
+                                                          pairs ? s->cl_count : nullptr);
+    CK_LAUNCH(); s->launches++;
+    s->launches += exclusive_scan<unsigned long long>(s->nbr_count, s->nbr_start, n, s->scan_tmp, st);
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, s->nbr_start + n, sizeof total, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&s->max_k, s->max_k_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+    int rc = alloc_tile_lists(s, st);                                   // synchronises: total / max_k are on the host too
+    if (rc) return rc;
+    s->total_pairs = (long long)total;
+    if (s->total_pairs > s->nbr_cap) {
+        if (s->nbr) cudaFree(s->nbr);
+        s->nbr = nullptr;
+        CK(dalloc(&s->nbr, (size_t)s->total_pairs + 32));
+        s->nbr_cap = s->total_pairs;
+    }
+    k_bits_expand<0><<<nblk((long long)n * 32, 256), 256, 0, st>>>(t.bits, W, s->cell_lin_sorted, s->cell_start, t.pos, t.tab, n, s->nbr_start, s->nbr,
+                                                                  s->nbr_count, t.blk_start, t.t_off, t.lists);
+    CK_LAUNCH(); s->launches++;
+    if (pairs) {
+        const int nc = (n + 1) / 2;
+        // clusters that straddle a cell boundary: union from the members' exact lists (count, then fill after the scan)
+        k_cluster_merge<2><<<nblk((long long)nc * 32, 128), 128, 0, st>>>(s->x0m, s->nbr_start, s->nbr, n, s->d2_limit, 0, s->cl_start, s->cl, s->cl_count,
+                                                                          s->cell_lin_sorted);
+        CK_LAUNCH(); s->launches++;
+        s->launches += exclusive_scan<unsigned long long>(s->cl_count, s->cl_start, nc, s->scan_tmp, st);
+        unsigned long long ct = 0;
+        CK(cudaMemcpyAsync(&ct, s->cl_start + nc, sizeof ct, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        s->cl_total = (long long)ct;
+        if (s->cl_total > s->cl_cap || !s->cl) {
+            if (s->cl) cudaFree(s->cl);
+            s->cl = nullptr;
+            CK(dalloc(&s->cl, (size_t)s->cl_total + LIST_PAD));
+            s->cl_cap = s->cl_total;
+        }
+        CK(cudaMemsetAsync(s->cl + s->cl_total, 0, (size_t)LIST_PAD * sizeof(uint32_t), st));      // the zero entries the force kernel may read past the last list
+        k_bits_expand<1><<<nblk((long long)nc * 32, 256), 256, 0, st>>>(t.bits, W, s->cell_lin_sorted, s->cell_start, t.pos, t.tab, n, s->cl_start, s->cl,
+                                                                       nullptr, nullptr, nullptr, nullptr);
+        k_cluster_merge<2><<<nblk((long long)nc * 32, 128), 128, 0, st>>>(s->x0m, s->nbr_start, s->nbr, n, s->d2_limit, 1, s->cl_start, s->cl, s->cl_count,
+                                                                          s->cell_lin_sorted);
+        CK_LAUNCH(); s->launches += 2;
+    } else {
+        rc = build_cluster_lists(s, st);
+        if (rc) return rc;
+    }
+    if (t.cap_d && t.cap_f) return finish_tiles(s, st);
     return MIS_OK;
 }
 static TileView make_tile_view(MisSim* s) {
@@ -484,31 +578,40 @@ extern "C" int mis_build_neighbors(MisSim* s, void* stream) {
         k_apply_order<<<nblk(n, 256), 256, 0, st>>>(s->perm, s->x0_orig, n, s->inv_perm, s->x0m);
         CK_LAUNCH(); s->launches += 2;
     }
-    CK(cudaMemsetAsync(s->max_k_dev, 0, sizeof(int), st));
-    k_nbr_walk<<<nblk(n, 128), 128, 0, st>>>(s->x0m, s->cell_lin_sorted, s->cell_start, s->cell_end, cdim, n, s->d2_limit, 0,
-                                             nullptr, nullptr, s->nbr_count, s->max_k_dev);
-    CK_LAUNCH(); s->launches++;
-    s->launches += exclusive_scan<unsigned long long>(s->nbr_count, s->nbr_start, n, s->scan_tmp, st);
-    CK_LAUNCH();
-    unsigned long long total = 0;
-    CK(cudaMemcpyAsync(&total, s->nbr_start + n, sizeof total, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&s->max_k, s->max_k_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    s->total_pairs = (long long)total;
-    if (s->total_pairs > s->nbr_cap) {
-        if (s->nbr) cudaFree(s->nbr);
-        s->nbr = nullptr;
-        CK(dalloc(&s->nbr, (size_t)s->total_pairs + 32));
-        s->nbr_cap = s->total_pairs;
-    }
-    k_nbr_walk<<<nblk(n, 128), 128, 0, st>>>(s->x0m, s->cell_lin_sorted, s->cell_start, s->cell_end, cdim, n, s->d2_limit, 1,
-                                             s->nbr_start, s->nbr, s->nbr_count, s->max_k_dev);
-    CK_LAUNCH(); s->launches++;
-    int rc = build_cluster_lists(s, st);
+    s->tile.ok = false; s->tile.tab_ok = false;
+    int rc = build_tile_tab(s, st);
     if (rc) return rc;
+    static const bool force_walk = env_int("MIS_BUILD_WALK", 0) != 0;          // A/B: the per-thread 27-cell walks of round 1
+    if (s->tile.max_tile <= 32 * TB_MAX_WORDS && !force_walk) {
+        rc = build_lists_tiled(s, st);
+        if (rc) return rc;
+    } else {
+        CK(cudaMemsetAsync(s->max_k_dev, 0, sizeof(int), st));
+        k_nbr_walk<<<nblk(n, 128), 128, 0, st>>>(s->x0m, s->cell_lin_sorted, s->cell_start, s->cell_end, cdim, n, s->d2_limit, 0,
+                                                 nullptr, nullptr, s->nbr_count, s->max_k_dev);
+        CK_LAUNCH(); s->launches++;
+        s->launches += exclusive_scan<unsigned long long>(s->nbr_count, s->nbr_start, n, s->scan_tmp, st);
+        CK_LAUNCH();
+        unsigned long long total = 0;
+        CK(cudaMemcpyAsync(&total, s->nbr_start + n, sizeof total, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&s->max_k, s->max_k_dev, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        s->total_pairs = (long long)total;
+        if (s->total_pairs > s->nbr_cap) {
+            if (s->nbr) cudaFree(s->nbr);
+            s->nbr = nullptr;
+            CK(dalloc(&s->nbr, (size_t)s->total_pairs + 32));
+            s->nbr_cap = s->total_pairs;
+        }
+        k_nbr_walk<<<nblk(n, 128), 128, 0, st>>>(s->x0m, s->cell_lin_sorted, s->cell_start, s->cell_end, cdim, n, s->d2_limit, 1,
+                                                 s->nbr_start, s->nbr, s->nbr_count, s->max_k_dev);
+        CK_LAUNCH(); s->launches++;
+        rc = build_cluster_lists(s, st);
+        if (rc) return rc;
+        if (s->tile.want_d || s->tile.want_f) { rc = build_tiles(s, st); if (rc) return rc; }
+    }
     drop_graph(s);                            // a captured chunk holds the old list pointers
     s->built = true;
-    if (s->tile.want_d || s->tile.want_f) { rc = build_tiles(s, st); if (rc) return rc; }
     return MIS_OK;
 }
 
@@ -770,7 +873,6 @@ extern "C" int mis_set_dirichlet(MisSim* s, const float* free_dev, void* stream)
 }
 
 // ------------------------------------------------------------------ step machinery
-static int env_int(const char* name, int dflt) { const char* e = getenv(name); return e && e[0] ? atoi(e) : dflt; }
 template <int C, int G> static void launch_deform(MisSim* s, const View& v, cudaStream_t st) {
     const int nc = (s->n + C - 1) / C;
     static int carve_dev[64];                 // tuning hook: MIS_DEFORM_CARVEOUT = preferred shared-memory carve-out in percent (a per-device attribute)

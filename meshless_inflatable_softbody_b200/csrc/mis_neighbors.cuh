@@ -245,12 +245,19 @@ template <int C>
 __global__ void __launch_bounds__(128) k_cluster_merge(const float4* __restrict__ x0m, const unsigned long long* __restrict__ nbr_start,
                                                        const uint32_t* __restrict__ nbr, int n, float d2_limit, int fill,
                                                        const unsigned long long* __restrict__ cl_start, uint32_t* __restrict__ cl,
-                                                       uint32_t* __restrict__ cl_count) {
+                                                       uint32_t* __restrict__ cl_count,
+                                                       const int* __restrict__ cell_lin_sorted = nullptr /* given: only clusters that straddle a cell boundary */) {
     const int nc = (n + C - 1) / C;
     const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (c >= nc) return;
     const int i0 = c * C;
     const int m = min(C, n - i0);
+    if (cell_lin_sorted && m == C) {          // clusters inside one cell get their union from the tile bitmasks (mis_tilebuild.cuh)
+        bool same = true;
+#pragma unroll
+        for (int q = 1; q < C; q++) same = same && cell_lin_sorted[i0 + q] == cell_lin_sorted[i0];
+        if (same) return;
+    }
     float4 p[C];
 #pragma unroll
     for (int q = 0; q < C; q++) p[q] = x0m[min(i0 + q, n - 1)];

@@ -54,9 +54,9 @@ __device__ __forceinline__ void t_mbar_wait(uint32_t bar, uint32_t parity) {
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"     // suspend-time hint: a waiting warp sleeps instead of
+            "selp.u32 %0, 1, 0, p;\n\t"                                           // spinning through the issue slots of the SM's other CTAs
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     } while (!done);
 }
 __device__ __forceinline__ void t_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
@@ -84,8 +84,7 @@ __global__ void __launch_bounds__(256) k_tile_flag(const int* __restrict__ cell_
 // one warp per first slot: the table row of that cell.  max_out[0] = largest tile, [1] = largest own count
 __global__ void __launch_bounds__(256) k_tile_tab(const uint32_t* __restrict__ flag, const unsigned long long* __restrict__ pos,
                                                   const int* __restrict__ cell_lin_sorted, const int* __restrict__ cell_start,
-                                                  const int* __restrict__ cell_end, int3 cdim, int n, int* __restrict__ tab, int* __restrict__ max_out,
-                                                  const unsigned long long* __restrict__ nbr_start, uint32_t* __restrict__ work_key, uint32_t* __restrict__ work_val) {
+                                                  const int* __restrict__ cell_end, int3 cdim, int n, int* __restrict__ tab, int* __restrict__ max_out) {
     const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (s >= n || !flag[s]) return;
     const int k = (int)pos[s];
@@ -110,13 +109,6 @@ __global__ void __launch_bounds__(256) k_tile_tab(const uint32_t* __restrict__ f
     if (lane == 28) row[TT_CELL] = lin;
     if (lane == 13) { row[TT_OWN_START] = start; row[TT_OWN_COUNT] = cnt; atomicMax(max_out + 1, cnt); }
     if (lane == 0) atomicMax(max_out, total);
-    // sort key of the longest-first launch order: pairs of the cell (its slots are contiguous, so are their lists)
-    const int own_start = __shfl_sync(0xffffffffu, start, 13), own_cnt = __shfl_sync(0xffffffffu, cnt, 13);
-    if (lane == 0) {
-        const unsigned long long pairs = nbr_start[own_start + own_cnt] - nbr_start[own_start];
-        work_key[k] = 0x000fffffu - (uint32_t)(pairs < 0x000fffffull ? pairs : 0x000fffffull);      // ascending sort = descending work
-        work_val[k] = (uint32_t)k;
-    }
 }
 // blocks per particle
 __global__ void __launch_bounds__(256) k_tile_count(const uint32_t* __restrict__ nbr_count, int n, uint32_t* __restrict__ nblocks) {

@@ -236,9 +236,12 @@ def cpu_side_rates(cfg, n_small=3000, n_hoisted=20000, seed=0):
 
 
 def size_cpu_sample(cfg, n_full, total_steps, budget_s):
-    rate, dt, cores, n0, _ = cpu_faithful_rate(cfg, 4000, 1, 0, with_obstacle=False)
+    """Particles the timed sample may hold so that `total_steps` steps take ~budget_s: calibrated on one step of a 16k-particle
+    sphere after one warm-up step (a 4k-particle probe under-reads the rate 2-3x -- thread start-up, first-touch -- and would
+    shrink the sample, and with it the CPU's rate, below what the budget allows)."""
+    rate, dt, cores, n0, _ = cpu_faithful_rate(cfg, 16000, 1, 1, with_obstacle=False)
     n_fit = int(rate * budget_s / max(1, total_steps))
-    return max(2000, min(n_full, n_fit)), rate
+    return max(8000, min(n_full, n_fit)), rate
 
 
 def resolve_mode(args, world):

@@ -1,4 +1,4 @@
-"""Short single-GPU command for ncu: the bench workload (sphere on a DeepSDF octahedron), a few un-graphed steps."""
+"""Short single-GPU command for ncu: the configs[1] workload (100k sphere on the DeepSDF plateau obstacle), a few un-graphed steps."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
@@ -12,7 +12,7 @@ sim = Simulator(x0, cfg, graph_steps=-1)
 net = DeepSDF(bench.obstacle_state())
 sim.set_sdf_obstacle(net, bbox_model=bench.obstacle_bbox(cfg), fd_eps=1e-4)
 sim.startup()
-sim.step(40)          # reach first contact
+sim.step(60)          # the sphere has landed on the plateau: ~100 particles in the contact band
 for _ in range(steps):
     sim.step(1)
 sim.synchronize()

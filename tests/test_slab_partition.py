@@ -192,3 +192,23 @@ def test_plan_invariants_on_a_regular_lattice_with_ties():
                 assert all(j in local for j in nb[i])
             for q, ids in p.recv.items():
                 assert np.array_equal(p.local_ids[ids], part.plans[q].owned[part.plans[q].send[p.rank]])
+
+
+def test_cost_weighted_cuts_shift_particles_away_from_loaded_ranks():
+    """SlabPartition.build(extra_cost=...): owned_r + extra_cost_r is equalised; every particle still has exactly one owner and the
+    ghost layers still cover the support radius."""
+    rng = np.random.default_rng(3)
+    x0 = rng.uniform(0.0, 1.0, (60000, 3)).astype(np.float32)
+    x0[:, 0] *= 4.0
+    base = SlabPartition.build(x0, 0.007, 4)
+    w = SlabPartition.build(x0, 0.007, 4, extra_cost=[0, 4000, 4000, 0])
+    assert [p.n_owned for p in base.plans] == [15000] * 4
+    assert [p.n_owned for p in w.plans] == [17000, 13000, 13000, 17000]
+    owner = np.full(len(x0), -1)
+    for p in w.plans:
+        assert (owner[p.owned] == -1).all()
+        owner[p.owned] = p.rank
+    assert (owner >= 0).all()
+    for p in w.plans:                         # every send list has a matching receive list of the same length
+        for q, ids in p.send.items():
+            assert len(ids) == len(w.plans[q].recv[p.rank])

@@ -477,7 +477,7 @@ def kernel_roofline(core, info, Kp, peaks, peak_src):
 def slab_parity_check(args, cfg, hz, rank, world, dev):
     """Every N > 1 line: a >= 200k-particle body dropped on the ground plane (impact from step ~30, elastic waves cross every cut)
     through the SAME slab machinery, against a single-domain run on rank 0.  Tolerance: 4 x the single-domain fp32 summation-order
-    floor (two cluster shapes and gather modes) + (4e-9, 2e-5)."""
+    floor (four cluster shapes / gather modes) + (4e-9, 2e-5)."""
     torch = hz.torch
     from meshless_inflatable_softbody_b200 import Simulator, scenes
     from meshless_inflatable_softbody_b200.slab import SlabSimulator

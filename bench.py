@@ -363,7 +363,13 @@ def measure(args, cfg, hz, stepper, core, n_total, n_io, has_obstacle, any_obsta
             c = core.contact_counts()
             cand_sum += c[0]; band_sum += c[1]
     hz.barrier()
-    ms_flushed = hz.max_over_ranks(sum(a.elapsed_time(b) for a, b in evs))
+    ms_own = sum(a.elapsed_time(b) for a, b in evs)
+    if hz.world > 1:                        # every rank's own device time (the halo flag waits are inside it): who paces the step
+        t = torch.zeros(hz.world, device=dev, dtype=torch.float64)
+        t[hz.dist.get_rank()] = ms_own / K
+        hz.dist.all_reduce(t, op=hz.dist.ReduceOp.SUM)
+        out["ms_per_step_by_rank"] = [round(float(v), 4) for v in t.tolist()]
+    ms_flushed = hz.max_over_ranks(ms_own)
     out["launches"] = core.launch_count - launches0
     cand_avg, band_avg = [v / K for v in hz.sum_over_ranks([cand_sum, band_sum])]
     out["contact"] = {"broad_phase_candidates_avg": cand_avg, "in_contact_band_avg": band_avg,
@@ -619,6 +625,8 @@ def run_ours(args, cfg, rank, world, local_rank):
         "gpu_launches": int(m["launches"]), "clocks": clocks, "roofline": roofline,
         "state_finite": m["state_finite"], "state_finite_at_end": m["state_finite_at_end"],
     }
+    if "ms_per_step_by_rank" in m:
+        line["ms_per_step_by_rank"] = m["ms_per_step_by_rank"]
     line.update(extra)
     if world > 1:
         line["parity_check"] = parity

@@ -177,7 +177,13 @@ __device__ __forceinline__ void tile_issue(unsigned char* smem, const int* __res
         }
     }
 }
-__device__ __forceinline__ void tile_wait(unsigned char* smem) { t_mbar_wait(t_smem_u32(smem), 0); }
+// One warp polls the mbarrier; the others park on the CTA barrier (no issue slots: a spinning CTA took 7.6 % of the deformation
+// kernel's executed instructions away from the SM's other CTAs).  The bulk copies' writes are visible to the polling warp through
+// the mbarrier's acquire and to everyone else through the barrier that follows it.
+__device__ __forceinline__ void tile_wait(unsigned char* smem) {
+    if (threadIdx.x < 32) t_mbar_wait(t_smem_u32(smem), 0);
+    __syncthreads();
+}
 template <int CAP, int NP>
 __device__ __forceinline__ void tile_load(unsigned char* smem, const int* __restrict__ tab_row, const float4* const (&plane)[NP]) {
     tile_issue<CAP, NP>(smem, tab_row, plane);

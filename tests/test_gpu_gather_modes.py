@@ -108,3 +108,28 @@ def test_fp64_scene_refuses_what_it_does_not_implement():
     f32 = torch.empty((len(x0), 3), dtype=torch.float32).pin_memory()
     with pytest.raises(MisError, match="fp64"):
         sim.get_state_host(f32, f32.clone())
+
+
+@pytest.mark.parametrize("n,spacing,expect_tiles", [(8000, 0.4, False), (7000, 0.3, False), (4000, 0.5, True)])
+def test_dense_clouds_fall_back_and_stay_exact(n, spacing, expect_tiles):
+    """A 27-cell neighbourhood of more than 2816 particles does not fit the force tile (more than 4096: not even the bitmask
+    build): the scene runs on the cluster kernels, the lists stay bit-equal to the oracle's, the step stays on the oracle's track."""
+    x0, _ = scenes.jittered_sphere(n, seed=5, spacing=spacing)
+    cfg = SceneConfig(youngs_modulus=1.5e4)            # 400-800 neighbours per particle: keep the explicit step stable
+    sim, o = Simulator(x0, cfg), make_oracle(x0, cfg)
+    info = sim.gather_info()
+    assert (info["mode"] == 2) == expect_tiles, info
+    off, nb = (_np(t) for t in sim.neighbors())
+    cnt, ooff, oflat = o.neighbor_lists()
+    assert np.array_equal(np.diff(off), cnt)
+    rows = np.repeat(np.arange(len(x0)), cnt)
+    assert np.array_equal(nb[np.lexsort((nb, rows))], oflat)
+    if not expect_tiles:
+        with pytest.raises(MisError, match="tile"):
+            sim.set_gather_mode(2)
+    b = make_oracle(x0, cfg); b.set_order(1)
+    sim.startup(); o.startup(); b.startup()
+    sim.step(10); o.step(10); b.step(10)
+    x, v = sim.position_velocity()
+    assert np.abs(_np(x) - o.position()).max() <= FLOOR_MULT * np.abs(o.position() - b.position()).max() + 4e-9
+    assert np.abs(_np(v) - o.velocity()).max() <= FLOOR_MULT * np.abs(o.velocity() - b.velocity()).max() + 2e-5

@@ -530,6 +530,7 @@ class Simulator:
     def kernel_names(self):
         """Names of the two gather kernels the step launches (what profile_step times; keys of profiles/traffic.json)."""
         mode = self.gather_info()["mode"]
+        # scenes of >= 1500 clusters per SM run the force gather from per-SM cluster queues (k_force_p): same arithmetic, same lists
         return {"k_deform": "k_deform_t" if mode else "k_deform_c", "k_force": "k_force_t" if mode == 1 else "k_force_c"}
 
     @property

@@ -605,6 +605,13 @@ def run_ours(args, cfg, rank, world, local_rank):
     if net:
         stepper.set_sdf_obstacle(None, None)           # per-kernel timing of the two gather kernels alone
     roofline = kernel_roofline(core, info, min(K, 50), peaks, peak_src)
+    if world > 1:                           # every rank's gather-kernel time per step (no obstacle, no waits): the partition's balance
+        t = torch.zeros((world, 3), device=dev, dtype=torch.float64)
+        kk = roofline["kernels"]
+        names = core.kernel_names()
+        t[rank, 0] = kk[names["k_deform"]]["ms"]; t[rank, 1] = kk[names["k_force"]]["ms"]; t[rank, 2] = 1.0 if near else 0.0
+        hz.dist.all_reduce(t, op=hz.dist.ReduceOp.SUM)
+        extra["gather_ms_by_rank"] = [{"deform": round(float(a), 4), "force": round(float(b), 4), "obstacle": bool(c)} for a, b, c in t.tolist()]
     if net:
         m_rows = 16384
         ms_gemm = net.profile_gemm(m_rows, reps=20)

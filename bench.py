@@ -564,17 +564,21 @@ def run_ours(args, cfg, rank, world, local_rank):
     if world > 1:
         parity = slab_parity_check(args, cfg, hz, rank, world, dev)
         extra_cost = None
+        weights = None
+        if args.balance == "pairs":         # cut by estimated pair work (27-cell occupancy), not by particle count
+            from meshless_inflatable_softbody_b200.slab import neighbour_weights
+            weights = neighbour_weights(x0, cfg.h)
         if use_obstacle and args.contact_cost > 0:
             # static load balance: the ranks whose slab lies under the obstacle run its MLP query every step (a latency-bound
             # ~0.2 ms that does not shrink with the slab); they own that many particle-equivalents fewer
             from meshless_inflatable_softbody_b200.slab import SlabPartition
-            cuts = SlabPartition.build(x0, cfg.h, world).cuts
+            cuts = SlabPartition.build(x0, cfg.h, world, weights=weights).cuts
             bb = np.asarray(obstacle_bbox(cfg), np.float64).reshape(2, 3)
             lo, hi = bb[0, 0] - 0.03, bb[1, 0] + 0.03
             extra_cost = np.array([args.contact_cost if (cuts[r] <= hi and cuts[r + 1] >= lo) else 0.0 for r in range(world)])
-        stepper = SlabSimulator(x0, cfg, rank=rank, world_size=world, device=str(dev), halo=args.halo, extra_cost=extra_cost, **sim_kw)
+        stepper = SlabSimulator(x0, cfg, rank=rank, world_size=world, device=str(dev), halo=args.halo, extra_cost=extra_cost, weights=weights, **sim_kw)
         core = stepper.sim
-        extra = {"partition_extra_cost_particles": extra_cost.tolist() if extra_cost is not None else None,
+        extra = {"partition_extra_cost_particles": extra_cost.tolist() if extra_cost is not None else None, "partition_balance": args.balance,
                  "halo": ("fused P2P push over NVLink peer memory from the force kernel's epilogue + epoch flags, inside the step graph"
                           if stepper.halo == "p2p" else "NCCL send/recv after every step"),
                  "owned_per_gpu": stepper.n_owned, "ghosts_per_gpu": core.n - stepper.n_owned,
@@ -827,6 +831,8 @@ def main():
     ap.add_argument("--contact-cost", type=float, default=100_000.0,
                     help="N > 1: per-step cost of the obstacle query in particle-equivalents (0.2 ms at 1.9 ns per particle-step); the ranks under "
                          "the obstacle own that many particles fewer (0 = equal counts)")
+    ap.add_argument("--balance", default="pairs", choices=["pairs", "count"],
+                    help="N > 1: slab cuts equalise the estimated pair work (27-cell occupancy per particle) or the particle count")
     ap.add_argument("--parity-n", type=int, default=200_000, help="N > 1: particles of the slab-vs-single-domain parity check")
     ap.add_argument("--e2e-steps", type=int, default=50)
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")

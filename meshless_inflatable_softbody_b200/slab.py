@@ -59,14 +59,19 @@ class SlabPartition:
 
     @classmethod
     def build(cls, x0: np.ndarray, h: float, world_size: int, axis: Optional[int] = None, ghost_layers: int = 2,
-              extra_cost: Optional[np.ndarray] = None) -> "SlabPartition":
+              extra_cost: Optional[np.ndarray] = None, weights: Optional[np.ndarray] = None) -> "SlabPartition":
         """Cut planes at quantiles of the x0 coordinate along `axis` (equal owned counts, to the particle); ghost layer L of a
         rank = foreign particles within L * 2h of its slab along the axis.  Every neighbour (|x0_i - x0_j| < 2h, sim.py:137-141)
         of an owned particle is owned or layer 1; every neighbour of a layer-1 ghost is local.
 
         extra_cost[r]: fixed per-step work of rank r that is not proportional to its particle count (e.g. the obstacle's MLP
         query, which only the ranks under the obstacle run), in particle-equivalents: the cuts then equalise
-        owned_r + extra_cost[r] instead of owned_r.  The partition is static, so this is a one-off load balance."""
+        owned_r + extra_cost[r] instead of owned_r.  The partition is static, so this is a one-off load balance.
+
+        weights[i]: relative per-step work of particle i (default 1).  The gather kernels' work is proportional to a particle's
+        neighbour count, which is lower near the surface: `neighbour_weights(x0, h)` estimates it from the 27-cell occupancy, so
+        that the tapered end slabs of a body own more particles than the full-section slabs in the middle.  extra_cost is then in
+        units of the mean weight."""
         x0 = np.asarray(x0, np.float32).reshape(-1, 3)
         n = len(x0)
         if axis is None:
@@ -80,9 +85,12 @@ class SlabPartition:
         owned_target = np.maximum(share - extra, 0.0)
         owned_target *= n / owned_target.sum()
         bounds = np.concatenate([[0.0], np.cumsum(owned_target)])
+        if weights is not None:                                      # cumulative work along the axis instead of particle counts
+            w = np.asarray(weights, np.float64).reshape(n)[order]
+            cw = np.cumsum(w) * (n / w.sum())                        # same scale as a particle count
         cuts = [-np.inf]
         for r in range(1, world_size):
-            k = int(round(bounds[r]))
+            k = int(round(bounds[r])) if weights is None else int(np.searchsorted(cw, bounds[r]))
             k = min(max(k, 1), n - 1)
             cuts.append(0.5 * (cs[k - 1] + cs[k]) if cs[k] > cs[k - 1] else cs[k])
         cuts.append(np.inf)
@@ -123,6 +131,25 @@ class SlabPartition:
                 gl = p.ghosts[sel]                                                # their global ids (ascending)
                 plans[q].send[p.rank] = np.searchsorted(plans[q].owned, gl).astype(np.int64)   # local (= owned index) on the sender
         return cls(axis=axis, cuts=cuts, plans=plans)
+
+
+def neighbour_weights(x0: np.ndarray, h: float) -> np.ndarray:
+    """Per-particle work estimate for SlabPartition.build(weights=...): the number of particles in the 27 cells (width 2h) around
+    a particle's cell -- proportional, on average, to its neighbour count (support radius 2h), hence to its share of the gather
+    kernels' pair evaluations.  Host numpy, one pass over the particles."""
+    x0 = np.asarray(x0, np.float32).reshape(-1, 3)
+    cw = 2.0 * float(np.float32(h))
+    ijk = np.floor(x0.astype(np.float64) / cw).astype(np.int64)
+    ijk -= ijk.min(0)
+    dims = ijk.max(0) + 3                                            # one empty cell of padding on every side
+    lin = ((ijk[:, 2] + 1) * dims[1] + (ijk[:, 1] + 1)) * dims[0] + (ijk[:, 0] + 1)
+    occ = np.bincount(lin, minlength=int(dims.prod())).astype(np.float64).reshape(dims[2], dims[1], dims[0])
+    nb = np.zeros_like(occ)
+    for dz in (-1, 0, 1):                                            # 27-cell box sum (separable would do; the grid is small)
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                nb += np.roll(occ, (dz, dy, dx), axis=(0, 1, 2))
+    return nb.reshape(-1)[lin]
 
 
 def exchange_halo(plan: RankPlan, gather, scatter, dist=None, group=None, device=None):
@@ -241,7 +268,7 @@ class SlabSimulator:
 
     def __init__(self, x0_global, config=None, rank: int = 0, world_size: int = 1, device: str = "cuda:0",
                  group=None, partition: Optional[SlabPartition] = None, in_process: bool = False, halo: str = "auto",
-                 extra_cost=None, **sim_kw):
+                 extra_cost=None, weights=None, **sim_kw):
         import torch
         import torch.distributed as dist
         from .config import SceneConfig
@@ -252,7 +279,7 @@ class SlabSimulator:
         self.dist, self.group = dist, group
         x0_global = np.asarray(x0_global, np.float32).reshape(-1, 3)
         self.n_global = len(x0_global)
-        self.partition = partition or SlabPartition.build(x0_global, self.cfg.h, world_size, extra_cost=extra_cost)
+        self.partition = partition or SlabPartition.build(x0_global, self.cfg.h, world_size, extra_cost=extra_cost, weights=weights)
         self.plan = self.partition.plans[rank]
         self.device = torch.device(device)
         local = self.plan.local_ids

@@ -212,3 +212,25 @@ def test_cost_weighted_cuts_shift_particles_away_from_loaded_ranks():
     for p in w.plans:                         # every send list has a matching receive list of the same length
         for q, ids in p.send.items():
             assert len(ids) == len(w.plans[q].recv[p.rank])
+
+
+def test_pair_work_weights_move_the_cuts_towards_the_full_sections():
+    """neighbour_weights: 27-cell occupancy per particle; with it the tapered end slabs of an ellipsoid own more particles and every
+    rank carries the same estimated pair work."""
+    from meshless_inflatable_softbody_b200 import scenes
+    from meshless_inflatable_softbody_b200.slab import neighbour_weights
+    x0 = scenes.jittered_ellipsoid(120_000, seed=1, aspect=(6.0, 1.0, 1.0)).astype(np.float32)
+    w = neighbour_weights(x0, 0.007)
+    assert w.shape == (len(x0),) and w.min() >= 1
+    # brute-force check of the estimate on a few particles
+    cw = 2 * float(np.float32(0.007))
+    cells = np.floor(x0.astype(np.float64) / cw).astype(np.int64)
+    for i in (0, 1234, len(x0) - 1):
+        assert w[i] == np.sum(np.all(np.abs(cells - cells[i]) <= 1, axis=1))
+    a = SlabPartition.build(x0, 0.007, 4)
+    b = SlabPartition.build(x0, 0.007, 4, weights=w)
+    na, nb = [p.n_owned for p in a.plans], [p.n_owned for p in b.plans]
+    assert max(na) - min(na) <= 1
+    assert nb[0] > nb[1] and nb[3] > nb[2] and sum(nb) == len(x0)
+    work = np.array([w[p.owned].sum() for p in b.plans])
+    assert work.max() / work.min() < 1.002

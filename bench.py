@@ -459,7 +459,8 @@ def kernel_roofline(core, info, Kp, peaks, peak_src):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
-            t = json.load(open(tpath)).get(core.kernel_names()[dom], {})
+            tj, kname = json.load(open(tpath)), core.kernel_names()[dom]
+            t = tj.get(kname) or tj.get(kname.replace("k_force_p", "k_force_c"), {})     # k_force_p streams k_force_c's lists and records
             per_particle = t.get("bytes_per_particle") or (t["bytes_per_launch_n100k"] / 99991.0 if "bytes_per_launch_n100k" in t else None)
             traffic = per_particle * nloc if per_particle else None      # ncu dram bytes per particle of the capture x particles of this launch
         except Exception:

@@ -125,6 +125,8 @@ struct MisSim {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_chain = nullptr;
     bool serial_contact = false;
     bool contact_first = true;                // MIS_CONTACT_FIRST=0: launch the deformation kernel at once instead of behind the chain's first layer
+    bool contact_split = false;               // the force gather stores fel (MODE_EVAL) and k_integrate follows the contact chain: the chain
+                                              // overlaps BOTH gather kernels (MIS_CONTACT_SPLIT=0/1; default: scenes of <= 400 k particles)
     // fused halo push (slab-partitioned scenes)
     int2* push = nullptr;                       // per-slot destination codes
     unsigned* halo_mem = nullptr;               // [0..MIS_MAX_PEERS) flags written by the peers, [MIS_MAX_PEERS] epoch, [MIS_MAX_PEERS + 1] error
@@ -377,7 +379,7 @@ static int build_tile_tab(MisSim* s, cudaStream_t st) {
     t.ok = false; t.tab_ok = false;
     if (!t.flag) {
         CK(dalloc(&t.flag, (size_t)n)); CK(dalloc(&t.pos, (size_t)n + 1)); CK(dalloc(&t.nblocks, (size_t)n));
-        CK(dalloc(&t.blk_start, (size_t)n + 1)); CK(dalloc(&t.t_off, (size_t)n)); CK(dalloc(&t.AB, 5 * (size_t)n)); CK(dalloc(&t.max_dev, 2));
+        CK(dalloc(&t.blk_start, (size_t)n + 1)); CK(dalloc(&t.t_off, (size_t)n)); CK(dalloc(&t.AB, 5 * (size_t)n)); CK(dalloc(&t.max_dev, 4));
         CK(dalloc(&t.wkey, (size_t)n)); CK(dalloc(&t.order, (size_t)n));
     }
     const int3 cdim = make_int3(s->cell_dim[0], s->cell_dim[1], s->cell_dim[2]);
@@ -395,7 +397,9 @@ static int build_tile_tab(MisSim* s, cudaStream_t st) {
         CK(dalloc(&t.tab, (size_t)t.n_active * TT_STRIDE));
         t.tab_cap = t.n_active;
     }
-    k_tile_tab<<<nblk((long long)n * 32, 256), 256, 0, st>>>(t.flag, t.pos, s->cell_lin_sorted, s->cell_start, s->cell_end, cdim, n, t.tab, t.max_dev);
+    const int by_cell = s->ncells <= n ? 1 : 0;
+    const int items = by_cell ? s->ncells : n;
+    k_tile_tab<<<nblk((long long)items * 32, 256), 256, 0, st>>>(t.flag, t.pos, s->cell_lin_sorted, s->cell_start, s->cell_end, cdim, items, by_cell, t.tab, t.max_dev);
     CK_LAUNCH(); s->launches++;
     int mx[2] = {0, 0};
     CK(cudaMemcpyAsync(mx, t.max_dev, sizeof mx, cudaMemcpyDeviceToHost, st));
@@ -471,6 +475,14 @@ static int build_lists_tiled(MisSim* s, cudaStream_t st) {
         t.bits_cap = (long long)n * W;
     }
     const bool pairs = s->C == 2 && !s->merge_lists;
+    int* straddle = reinterpret_cast<int*>(t.wkey);                      // n ints, free until finish_tiles: the clusters k_cluster_merge works on
+    int n_straddle = 0;
+    if (pairs) {
+        CK(cudaMemsetAsync(t.max_dev + 2, 0, sizeof(int), st));
+        k_straddle_list<<<nblk((n + 1) / 2, 256), 256, 0, st>>>(s->cell_lin_sorted, n, straddle, t.max_dev + 2);
+        CK_LAUNCH(); s->launches++;
+        CK(cudaMemcpyAsync(&n_straddle, t.max_dev + 2, sizeof(int), cudaMemcpyDeviceToHost, st));     // on the host after alloc_tile_lists' sync
+    }
     const int smem = tb_smem_bytes(W, t.max_own);
     CK(cudaFuncSetAttribute(k_tile_walk_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CK(cudaMemsetAsync(s->max_k_dev, 0, sizeof(int), st));
@@ -490,14 +502,24 @@ static int build_lists_tiled(MisSim* s, cudaStream_t st) {
         CK(dalloc(&s->nbr, (size_t)s->total_pairs + 32));
         s->nbr_cap = s->total_pairs;
     }
-    k_bits_expand<0><<<nblk((long long)n * 32, 256), 256, 0, st>>>(t.bits, W, s->cell_lin_sorted, s->cell_start, t.pos, t.tab, n, s->nbr_start, s->nbr,
-                                                                  s->nbr_count, t.blk_start, t.t_off, t.lists);
+    // per-cell expansion with warp staging buffers (mis_tilebuild.cuh) unless a list is longer than the staging capacity
+    const bool old_expand = env_int("MIS_BUILD_EXPAND_OLD", 0) != 0;           // A/B: the one-bit-per-lane expansion (read per build)
+    const bool cell_expand = s->max_k <= TX_MAX_K && !old_expand;
+    const int KP = ((s->max_k > 0 ? s->max_k : 1) + TILE_BLOCK - 1) / TILE_BLOCK * TILE_BLOCK;
+    if (cell_expand) {
+        CK(cudaFuncSetAttribute(k_tile_expand<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tx_smem_bytes(W, KP, 0)));
+        k_tile_expand<0><<<t.n_active, TX_THREADS, tx_smem_bytes(W, KP, 0), st>>>(t.bits, W, KP, t.tab, s->nbr_start, s->nbr, t.blk_start, t.t_off, t.lists);
+    } else {
+        k_bits_expand<0><<<nblk((long long)n * 32, 256), 256, 0, st>>>(t.bits, W, s->cell_lin_sorted, s->cell_start, t.pos, t.tab, n, s->nbr_start, s->nbr,
+                                                                      s->nbr_count, t.blk_start, t.t_off, t.lists);
+    }
     CK_LAUNCH(); s->launches++;
     if (pairs) {
         const int nc = (n + 1) / 2;
         // clusters that straddle a cell boundary: union from the members' exact lists (count, then fill after the scan)
-        k_cluster_merge<2><<<nblk((long long)nc * 32, 128), 128, 0, st>>>(s->x0m, s->nbr_start, s->nbr, n, s->d2_limit, 0, s->cl_start, s->cl, s->cl_count,
-                                                                          s->cell_lin_sorted);
+        if (n_straddle > 0)
+            k_cluster_merge<2><<<nblk((long long)n_straddle * 32, 128), 128, 0, st>>>(s->x0m, s->nbr_start, s->nbr, n, s->d2_limit, 0, s->cl_start, s->cl, s->cl_count,
+                                                                                      s->cell_lin_sorted, straddle, n_straddle);
         CK_LAUNCH(); s->launches++;
         s->launches += exclusive_scan<unsigned long long>(s->cl_count, s->cl_start, nc, s->scan_tmp, st);
         unsigned long long ct = 0;
@@ -511,10 +533,16 @@ static int build_lists_tiled(MisSim* s, cudaStream_t st) {
             s->cl_cap = s->cl_total;
         }
         CK(cudaMemsetAsync(s->cl + s->cl_total, 0, (size_t)LIST_PAD * sizeof(uint32_t), st));      // the zero entries the force kernel may read past the last list
-        k_bits_expand<1><<<nblk((long long)nc * 32, 256), 256, 0, st>>>(t.bits, W, s->cell_lin_sorted, s->cell_start, t.pos, t.tab, n, s->cl_start, s->cl,
-                                                                       nullptr, nullptr, nullptr, nullptr);
-        k_cluster_merge<2><<<nblk((long long)nc * 32, 128), 128, 0, st>>>(s->x0m, s->nbr_start, s->nbr, n, s->d2_limit, 1, s->cl_start, s->cl, s->cl_count,
-                                                                          s->cell_lin_sorted);
+        if (cell_expand) {
+            CK(cudaFuncSetAttribute(k_tile_expand<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tx_smem_bytes(W, KP, 1)));
+            k_tile_expand<1><<<t.n_active, TX_THREADS, tx_smem_bytes(W, KP, 1), st>>>(t.bits, W, KP, t.tab, s->cl_start, s->cl, nullptr, nullptr, nullptr);
+        } else {
+            k_bits_expand<1><<<nblk((long long)nc * 32, 256), 256, 0, st>>>(t.bits, W, s->cell_lin_sorted, s->cell_start, t.pos, t.tab, n, s->cl_start, s->cl,
+                                                                           nullptr, nullptr, nullptr, nullptr);
+        }
+        if (n_straddle > 0)
+            k_cluster_merge<2><<<nblk((long long)n_straddle * 32, 128), 128, 0, st>>>(s->x0m, s->nbr_start, s->nbr, n, s->d2_limit, 1, s->cl_start, s->cl, s->cl_count,
+                                                                                      s->cell_lin_sorted, straddle, n_straddle);
         CK_LAUNCH(); s->launches += 2;
     } else {
         rc = build_cluster_lists(s, st);
@@ -590,7 +618,7 @@ extern "C" int mis_build_neighbors(MisSim* s, void* stream) {
     int rc = build_tile_tab(s, st);
     if (rc) return rc;
     static const bool force_walk = env_int("MIS_BUILD_WALK", 0) != 0;          // A/B: the per-thread 27-cell walks of round 1
-    if (s->tile.max_tile <= 32 * TB_MAX_WORDS && !force_walk) {
+    if (s->tile.max_tile <= 32 * TB_MAX_WORDS && tb_smem_bytes(s->tile.W, s->tile.max_own) <= 227 * 1024 && !force_walk) {
         rc = build_lists_tiled(s, st);
         if (rc) return rc;
     } else {
@@ -1054,6 +1082,27 @@ static void enqueue_deform_contact(MisSim* s, const View& v, cudaStream_t st) {
     if (e != cudaSuccess && s->enqueue_err == cudaSuccess) s->enqueue_err = e;      // surfaced by mis_step / prime
 }
 
+// deformation + contact + force/integrate of one frame at the current positions
+static void enqueue_frame(MisSim* s, const View& v, int mode, cudaStream_t st) {
+    if (s->sdf && s->side_stream && !s->serial_contact && s->contact_split) {
+        // the contact chain on the side stream next to BOTH gather kernels; only the integration waits for it
+        cudaEventRecord(s->ev_fork, st);
+        cudaStreamWaitEvent(s->side_stream, s->ev_fork, 0);
+        cudaError_t e = enqueue_contact(s, v, s->side_stream, s->contact_first ? s->ev_chain : nullptr);
+        cudaEventRecord(s->ev_join, s->side_stream);
+        if (s->contact_first) cudaStreamWaitEvent(st, s->ev_chain, 0);
+        enqueue_deform(s, v, st);
+        enqueue_force(s, v, MODE_EVAL, st);
+        cudaStreamWaitEvent(st, s->ev_join, 0);
+        k_integrate<<<nblk(s->n, 256), 256, 0, st>>>(v, s->c, mode);
+        s->launches++;
+        if (e != cudaSuccess && s->enqueue_err == cudaSuccess) s->enqueue_err = e;
+        return;
+    }
+    enqueue_deform_contact(s, v, st);
+    enqueue_force(s, v, mode, st);
+}
+
 // frame-0 style priming at the current x: elastic force, force_1 and the next position
 static int prime(MisSim* s, cudaStream_t st) {
     if (!s->mass_set || !s->material_set) return fail(MIS_E_STATE, "set_mass and set_material must precede startup/step");
@@ -1065,8 +1114,7 @@ static int prime(MisSim* s, cudaStream_t st) {
             k_reintegrate<<<nblk(s->n, 256), 256, 0, st>>>(v, s->c);
             s->launches++;
         } else {
-            enqueue_deform_contact(s, v, st);
-            enqueue_force(s, v, MODE_PRIME, st);
+            enqueue_frame(s, v, MODE_PRIME, st);
         }
         enqueue_halo_sync(s, st);
         if (s->enqueue_err != cudaSuccess) { cudaError_t e = s->enqueue_err; s->enqueue_err = cudaSuccess; CK(e); }
@@ -1119,14 +1167,12 @@ static void enqueue_one_step(MisSim* s, cudaStream_t st) {
     if (s->p.euler) {
         // sim_taichi.py:174-182: forces at frame f, then advance to f+1
         View v = make_view(s);
-        enqueue_deform_contact(s, v, st);
-        enqueue_force(s, v, MODE_EULER, st);
+        enqueue_frame(s, v, MODE_EULER, st);
         s->cur ^= 1;
     } else {
         s->cur ^= 1;                       // part_1 of this step was fused into the previous force kernel
         View v = make_view(s);
-        enqueue_deform_contact(s, v, st);
-        enqueue_force(s, v, MODE_STEP, st);
+        enqueue_frame(s, v, MODE_STEP, st);
         enqueue_halo_sync(s, st);
     }
 }
@@ -1697,6 +1743,11 @@ extern "C" int mis_set_sdf_contact(MisSim* s, MisSdf* sdf, const float* xform_ho
         s->serial_contact = e && e[0] == '1';
         const char* f = getenv("MIS_CONTACT_FIRST");
         s->contact_first = !(f && f[0] == '0');
+    }
+    {   // The chain (~0.2 ms, latency-bound) hides behind the deformation kernel alone once that runs longer than the chain
+        // (n > ~3e5); below that the split buys the overlap with the force gather for one more pass over ~150 B per particle.
+        const int sp = env_int("MIS_CONTACT_SPLIT", -1);
+        s->contact_split = sp < 0 ? s->n <= 400000 : sp != 0;
     }
     CK(cudaMemsetAsync(s->con_count, 0, 4 * sizeof(int), (cudaStream_t)stream));
     {   // rows one pass of the chain can take: the activations are 16 KB per row (4 buffers x H floats), so the capacity is bounded

@@ -777,6 +777,16 @@ __global__ void __launch_bounds__(256) k_reintegrate(View s, Consts c) {
     integrate_epilogue(s, c, i, xyz(s.fel[i]), MODE_PRIME, s.x0m[i], s.xcur[i]);
 }
 
+// part_2 / part_1 (or the Euler update) from the STORED elastic force: the epilogue of the force kernel as its own launch.  Scenes
+// with an obstacle run the force gather in MODE_EVAL so that it does not have to wait for the contact chain (which only this
+// kernel's total force needs): same arithmetic, same operands, same results as the fused epilogue.
+__global__ void __launch_bounds__(256) k_integrate(View s, Consts c, int mode) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n) return;
+    if (s.push && s.push[i].x == PUSH_GHOST) return;               // ghosts are integrated by their owner
+    integrate_epilogue(s, c, i, xyz(s.fel[i]), mode, s.x0m[i], s.xcur[i]);
+}
+
 // ---------------------------------------------------------------- small per-particle kernels
 // gather caller-order arrays into cell-sorted slots
 __global__ void __launch_bounds__(256) k_gather_vec3(const float* __restrict__ src, const uint32_t* __restrict__ perm, int n, float4* __restrict__ dst, int keep_w) {

@@ -64,9 +64,16 @@ __global__ void __launch_bounds__(256) k_cell_coords(const float* __restrict__ x
         cy = min(cy, __shfl_xor_sync(0xffffffffu, cy, o)); my = max(my, __shfl_xor_sync(0xffffffffu, my, o));
         cz = min(cz, __shfl_xor_sync(0xffffffffu, cz, o)); mz = max(mz, __shfl_xor_sync(0xffffffffu, mz, o));
     }
+    // an atomic only where it would move the bound: after the first few warps almost none does (31 k warps x 6 atomics on six
+    // addresses serialised in L2 and were 90 % of this kernel's time at n = 1e6)
     if ((threadIdx.x & 31) == 0) {
-        atomicMin(bounds + 0, cx); atomicMin(bounds + 1, cy); atomicMin(bounds + 2, cz);
-        atomicMax(bounds + 3, mx); atomicMax(bounds + 4, my); atomicMax(bounds + 5, mz);
+        const volatile int* vb = bounds;
+        if (cx < vb[0]) atomicMin(bounds + 0, cx);
+        if (cy < vb[1]) atomicMin(bounds + 1, cy);
+        if (cz < vb[2]) atomicMin(bounds + 2, cz);
+        if (mx > vb[3]) atomicMax(bounds + 3, mx);
+        if (my > vb[4]) atomicMax(bounds + 4, my);
+        if (mz > vb[5]) atomicMax(bounds + 5, mz);
     }
 }
 
@@ -246,9 +253,15 @@ __global__ void __launch_bounds__(128) k_cluster_merge(const float4* __restrict_
                                                        const uint32_t* __restrict__ nbr, int n, float d2_limit, int fill,
                                                        const unsigned long long* __restrict__ cl_start, uint32_t* __restrict__ cl,
                                                        uint32_t* __restrict__ cl_count,
-                                                       const int* __restrict__ cell_lin_sorted = nullptr /* given: only clusters that straddle a cell boundary */) {
+                                                       const int* __restrict__ cell_lin_sorted = nullptr /* given: only clusters that straddle a cell boundary */,
+                                                       const int* __restrict__ list = nullptr /* given: warp w works on cluster list[w] */, int list_n = 0) {
     const int nc = (n + C - 1) / C;
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (list) {
+        if (c >= list_n) return;
+        c = list[c];
+    }
     if (c >= nc) return;
     const int i0 = c * C;
     const int m = min(C, n - i0);
@@ -288,6 +301,22 @@ __global__ void __launch_bounds__(128) k_cluster_merge(const float4* __restrict_
         }
     }
     if (!fill && lane == 0) cl_count[c] = count;
+}
+
+// clusters of two whose members sit in different cells, and a lone last particle: the work list of k_cluster_merge in the tiled
+// build (3 % of the clusters; a warp per cluster just to find that out cost 2 x 80 us at n = 1e6)
+__global__ void __launch_bounds__(256) k_straddle_list(const int* __restrict__ cell_lin_sorted, int n, int* __restrict__ list, int* __restrict__ count) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const int nc = (n + 1) / 2;
+    bool st = false;
+    if (c < nc) { const int a = 2 * c, b = a + 1; st = b >= n || cell_lin_sorted[a] != cell_lin_sorted[b]; }
+    const uint32_t m = __ballot_sync(0xffffffffu, st);
+    if (!m) return;
+    const int leader = __ffs((int)m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (st) list[base + __popc(m & ((1u << lane) - 1u))] = c;
 }
 
 // CSR export in caller ids: row i (caller id) <- row inv_perm[i] (sorted), entries mapped by perm

@@ -81,14 +81,25 @@ __global__ void __launch_bounds__(256) k_tile_flag(const int* __restrict__ cell_
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < n) flag[s] = cell_start[cell_lin_sorted[s]] == s ? 1u : 0u;
 }
-// one warp per first slot: the table row of that cell.  max_out[0] = largest tile, [1] = largest own count
+// the table row of every non-empty cell, one warp per cell.  by_cell: item = a cell of the dense table (compact scenes: fewer
+// cells than particles); else item = a slot, and the first slot of each cell does the work (sparse scenes whose dense table is
+// mostly empty).  max_out[0] = largest tile, [1] = largest own count
 __global__ void __launch_bounds__(256) k_tile_tab(const uint32_t* __restrict__ flag, const unsigned long long* __restrict__ pos,
                                                   const int* __restrict__ cell_lin_sorted, const int* __restrict__ cell_start,
-                                                  const int* __restrict__ cell_end, int3 cdim, int n, int* __restrict__ tab, int* __restrict__ max_out) {
-    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (s >= n || !flag[s]) return;
+                                                  const int* __restrict__ cell_end, int3 cdim, int items, int by_cell,
+                                                  int* __restrict__ tab, int* __restrict__ max_out) {
+    const int item = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (item >= items) return;
+    int lin, s;
+    if (by_cell) {
+        lin = item; s = cell_start[lin];
+        if (cell_end[lin] <= s) return;
+    } else {
+        s = item;
+        if (!flag[s]) return;
+        lin = cell_lin_sorted[s];
+    }
     const int k = (int)pos[s];
-    const int lin = cell_lin_sorted[s];
     const int cx = lin % cdim.x, cy = (lin / cdim.x) % cdim.y, cz = lin / (cdim.x * cdim.y);
     int start = 0, cnt = 0;
     if (lane < 27) {

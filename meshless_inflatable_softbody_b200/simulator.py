@@ -530,8 +530,14 @@ class Simulator:
     def kernel_names(self):
         """Names of the two gather kernels the step launches (what profile_step times; keys of profiles/traffic.json)."""
         mode = self.gather_info()["mode"]
-        # scenes of >= 1500 clusters per SM run the force gather from per-SM cluster queues (k_force_p): same arithmetic, same lists
-        return {"k_deform": "k_deform_t" if mode else "k_deform_c", "k_force": "k_force_t" if mode == 1 else "k_force_c"}
+        force = "k_force_t" if mode == 1 else "k_force_c"
+        # scenes of >= 1500 clusters per SM run the force gather from per-SM cluster queues (k_force_p): same arithmetic, same
+        # lists, another launch shape (enqueue_force in csrc/mis_api.cu; MIS_FORCE_PERSIST=0 switches it off)
+        if force == "k_force_c" and not self.cfg.symmetric_pair and os.environ.get("MIS_FORCE_PERSIST", "1")[:1] != "0":
+            nsm = torch.cuda.get_device_properties(self.device).multi_processor_count
+            if self.n // (int(self.params.cluster_size) or 2) >= 1500 * nsm:
+                force = "k_force_p"
+        return {"k_deform": "k_deform_t" if mode else "k_deform_c", "k_force": force}
 
     @property
     def launch_count(self) -> int:

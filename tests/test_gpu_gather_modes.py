@@ -133,3 +133,60 @@ def test_dense_clouds_fall_back_and_stay_exact(n, spacing, expect_tiles):
     x, v = sim.position_velocity()
     assert np.abs(_np(x) - o.position()).max() <= FLOOR_MULT * np.abs(o.position() - b.position()).max() + 4e-9
     assert np.abs(_np(v) - o.velocity()).max() <= FLOOR_MULT * np.abs(o.velocity() - b.velocity()).max() + 2e-5
+
+
+def _env(name, value):
+    class _E:
+        def __enter__(self):
+            self.old = os.environ.get(name)
+            os.environ[name] = value
+        def __exit__(self, *a):
+            if self.old is None:
+                os.environ.pop(name, None)
+            else:
+                os.environ[name] = self.old
+    return _E()
+
+
+@pytest.mark.parametrize("n", [3000, 20001])
+def test_cell_expansion_equals_the_bitwise_expansion(n):
+    """k_tile_expand (one CTA per cell, warp staging buffers) and k_bits_expand (MIS_BUILD_EXPAND_OLD=1) are two expansions of the
+    same bitmasks: identical exact lists, and -- because the uint16 tile lists and the cluster union lists then hold the same
+    entries in the same order -- bit-identical trajectories."""
+    x0, _ = scenes.jittered_sphere(n, seed=3, low_drop=True)
+    a = Simulator(x0, SceneConfig())
+    with _env("MIS_BUILD_EXPAND_OLD", "1"):
+        b = Simulator(x0, SceneConfig())
+    for u, w in zip(a.neighbors(), b.neighbors()):
+        assert torch.equal(u, w)
+    a.startup(); b.startup()
+    a.step(25); b.step(25)
+    (xa, va), (xb, vb) = a.position_velocity(), b.position_velocity()
+    assert torch.equal(xa, xb) and torch.equal(va, vb)
+    a.rebuild_neighbors(); a.step(5); b.step(5)                    # a rebuild reproduces the same lists (Total-Lagrangian)
+    (xa, va), (xb, vb) = a.position_velocity(), b.position_velocity()
+    assert torch.equal(xa, xb) and torch.equal(va, vb)
+
+
+def test_split_contact_integration_is_bit_identical():
+    """MIS_CONTACT_SPLIT: the force gather stores the elastic force and k_integrate follows the contact chain, instead of the
+    fused epilogue waiting for it.  Same operands, same operation order: the same bits."""
+    cfg = SceneConfig()
+    r, top = 0.05, 0.02
+    st = scenes.plateau_obstacle_state(r, top, hidden=1024, n_linear=9)
+    x0, _ = scenes.jittered_sphere(3000, seed=1)
+    x0[:, 1] += (top - 0.003) - x0[:, 1].min()
+    out = []
+    for split in ("0", "1"):
+        with _env("MIS_CONTACT_SPLIT", split):
+            net = DeepSDF(st)
+            sim = Simulator(x0, cfg)
+            sim.set_sdf_obstacle(net, bbox_model=scenes.plateau_obstacle_bbox(r, top, cfg.collision_range * np.sqrt(3.0) + 5e-4), fd_eps=1e-4)
+            sim.startup(); sim.step(40)
+            x, v = sim.position_velocity()
+            nb, nc = sim.contact_counts()
+            out.append((x.clone(), v.clone(), sim.contact_force().clone(), nc))
+            sim.close()
+    assert out[0][3] >= 8, "the scene is not in contact"
+    for u, w in zip(out[0][:3], out[1][:3]):
+        assert torch.equal(u, w)

@@ -436,7 +436,7 @@ static int finish_tiles(MisSim* s, cudaStream_t st) {
     MisSim::Tile& t = s->tile;
     k_tile_work<<<nblk(t.n_active, 256), 256, 0, st>>>(t.tab, t.n_active, s->nbr_start, t.wkey, t.order);
     CK_LAUNCH(); s->launches++;
-    s->launches += radix_sort_pairs(t.wkey, t.order, t.n_active, 20, s->rs, st);
+    s->launches += radix_sort_pairs(t.wkey, t.order, t.n_active, 16, s->rs, st);
     CK_LAUNCH();
     cudaError_t e = cudaSuccess;
     switch (t.cap_d) {

@@ -193,6 +193,9 @@ inline int radix_sort_pairs(uint32_t* keys, uint32_t* vals, int n, int bits, Rad
     if (passes < 1) passes = 1;
     if (passes & 1) passes++;
     int launches = 0;
+    int nb = (n + RS_TILE - 1) / RS_TILE;                 // t is sized for the largest sort; a short one (the tile launch order) runs short grids and scans
+    if (nb < 1) nb = 1;
+    if (nb > t.nblocks) nb = t.nblocks;
     for (int p = 0; p < passes; p++) {
         const bool even = (p & 1) == 0;
         const uint32_t* src_k = even ? keys : t.keys_alt;
@@ -200,9 +203,9 @@ inline int radix_sort_pairs(uint32_t* keys, uint32_t* vals, int n, int bits, Rad
         uint32_t* dst_k = even ? t.keys_alt : keys;
         uint32_t* dst_v = even ? t.vals_alt : vals;
         const int shift = 8 * p;
-        rs_histogram<<<t.nblocks, RS_THREADS, 0, st>>>(src_k, n, shift, t.hist, t.nblocks);
-        launches += 1 + exclusive_scan<uint32_t>(t.hist, t.hist_scanned, (long long)RS_RADIX * t.nblocks, t.tile_tmp, st);
-        rs_scatter<<<t.nblocks, RS_THREADS, 0, st>>>(src_k, src_v, dst_k, dst_v, n, shift, t.hist_scanned, t.nblocks);
+        rs_histogram<<<nb, RS_THREADS, 0, st>>>(src_k, n, shift, t.hist, nb);
+        launches += 1 + exclusive_scan<uint32_t>(t.hist, t.hist_scanned, (long long)RS_RADIX * nb, t.tile_tmp, st);
+        rs_scatter<<<nb, RS_THREADS, 0, st>>>(src_k, src_v, dst_k, dst_v, n, shift, t.hist_scanned, nb);
         launches++;
     }
     return launches;

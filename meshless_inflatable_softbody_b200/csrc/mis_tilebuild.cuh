@@ -103,90 +103,130 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_walk_bits(const uint32_t* _
 // ---------------------------------------------------------------- expansion, one CTA per cell
 // Mask bits -> list entries in ascending tile order.  The tile-index -> slot map is the same for every particle of a cell, so it
 // is built once per CTA in shared memory.  One warp per own particle (MODE 0) or per in-cell cluster of two (MODE 1, OR of the two
-// masks): lane l holds words l, l + 32, ... of the mask; a warp scan of the popcounts gives every word its first entry, each lane
-// then peels the bits of ITS words into a per-warp staging buffer, and the finished list leaves with coalesced 128-byte stores
-// (the one-bit-per-lane expansion it replaces issued ~20 instructions and two scattered stores for 4.6 entries per word).
+// masks).  The expansion is ENTRY-parallel: lane l produces entries l, l + 32, ... whatever the bit pattern -- the masks are
+// blobs (a tile word = 32 neighbouring records is mostly inside or mostly outside a support sphere), and a lane that peels the
+// bits of its own words ran at 11 of 32 lanes (ncu, 1 400 instructions per particle).  The unit is a BYTE of the mask: a warp
+// scan of the word popcounts (plus three popcounts inside the word) gives every byte its first entry; each non-empty byte
+// leaves its index as a marker at that entry, a running max-scan over the entries turns the markers into "byte of entry e", and
+// the entry's rank inside the byte picks the bit from a 256 x 8 table.  Stores go straight to global memory: slot ids
+// coalesced, the transposed uint16 blocks as 2-byte stores that fill a 128-byte block with two consecutive instructions
+// (merged in L2).
 // MODE 0 writes nbr (slot ids) and the transposed uint16 tile lists (pads = the particle itself), MODE 1 writes cl.
 constexpr int TX_THREADS = 256;
-constexpr int TX_MAX_K = 512;                  // staging capacity per warp: denser scenes take k_bits_expand
-__host__ __device__ inline int tx_smem_bytes(int W, int KP, int mode) { return TILE_HDR + W * 32 * 4 + (TX_THREADS / 32) * KP * (mode == 0 ? 6 : 8); }
+constexpr int TX_MAX_K = 1024;                 // marker capacity per warp (MODE 1: 2x): denser scenes take k_bits_expand
+constexpr int TX_LUT = 2048;                   // bytes: position of the r-th set bit of byte v at [8 v + r]
+// per warp: W words, 4 W uint16 byte offsets (= 2 W ints), cap markers
+__host__ __device__ inline int tx_warp_ints(int W, int KP, int mode) { return 3 * ((W + 1) & ~1) + (mode == 0 ? KP : 2 * KP); }   // W rounded to even: 8-byte rows
+__host__ __device__ inline int tx_smem_bytes(int W, int KP, int mode) {
+    return TILE_HDR + TX_LUT + W * 32 * 4 + (TX_THREADS / 32) * tx_warp_ints(W, KP, mode) * 4;
+}
 __device__ __forceinline__ int tile_list_pos(int e) { return (e & ~(TILE_BLOCK - 1)) | ((e % TILE_G) * 8) | ((e / TILE_G) & 7); }
 
 template <int MODE>
-__global__ void __launch_bounds__(TX_THREADS) k_tile_expand(const uint32_t* __restrict__ bits, int W, int KP /* multiple of TILE_BLOCK, >= max k */,
+__global__ void __launch_bounds__(TX_THREADS) k_tile_expand(const uint32_t* __restrict__ bits, int W, int KP /* >= the longest exact list */,
                                                             const int* __restrict__ tab, const unsigned long long* __restrict__ out_start,
                                                             uint32_t* __restrict__ out_slots, const unsigned long long* __restrict__ blk_start,
                                                             uint32_t* __restrict__ t_off, unsigned short* __restrict__ lists16) {
     static_assert(TILE_G == 8 && TILE_BLOCK == 64, "tile_list_pos");
+    static_assert(TX_THREADS == 256, "one thread per table row");
     extern __shared__ __align__(128) unsigned char smem[];
     int* row = reinterpret_cast<int*>(smem + 64);
     if (threadIdx.x < TT_STRIDE) row[threadIdx.x] = tab[(size_t)blockIdx.x * TT_STRIDE + threadIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cap = MODE == 0 ? KP : 2 * KP;
+    unsigned char* lut = smem + TILE_HDR;
+    uint32_t* map = reinterpret_cast<uint32_t*>(smem + TILE_HDR + TX_LUT);
+    uint32_t* s_wd = reinterpret_cast<uint32_t*>(smem + TILE_HDR + TX_LUT + (size_t)W * 32 * 4) + (size_t)warp * tx_warp_ints(W, KP, MODE);   // word w
+    const int Wp = (W + 1) & ~1;
+    unsigned short* s_pre = reinterpret_cast<unsigned short*>(s_wd + Wp);       // first entry of byte u (4 per word)
+    int* s_mk = reinterpret_cast<int*>(s_wd + 3 * Wp);                          // marker (u + 1) at the first entry of a non-empty byte u
+    for (int e = lane; e < cap; e += 32) s_mk[e] = 0;                    // every marker is cleared again by the entry that reads it
+    {
+        const uint32_t v = threadIdx.x;
+        unsigned long long pk = 0ull;
+        int r = 0;
+#pragma unroll
+        for (int b = 0; b < 8; b++)
+            if ((v >> b) & 1u) { pk |= (unsigned long long)b << (8 * r); r++; }
+        reinterpret_cast<unsigned long long*>(lut)[v] = pk;
+    }
     __syncthreads();
     const int own_start = row[TT_OWN_START], own_count = row[TT_OWN_COUNT], own_pref = row[TT_PREF + 13], total = row[TT_PREF + 27];
-    uint32_t* map = reinterpret_cast<uint32_t*>(smem + TILE_HDR);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int k = warp; k < 27; k += TX_THREADS / 32) {
         const int t0 = row[TT_PREF + k], t1 = row[TT_PREF + k + 1], s0 = row[k];
         for (int t = t0 + lane; t < t1; t += 32) map[t] = (uint32_t)(s0 + (t - t0));
     }
     __syncthreads();
     const int Wc = (total + 31) >> 5;
-    const int cap = MODE == 0 ? KP : 2 * KP;
-    uint32_t* st_slots = reinterpret_cast<uint32_t*>(smem + TILE_HDR + (size_t)W * 32 * 4 + (size_t)warp * KP * (MODE == 0 ? 6 : 8));
-    unsigned short* st16 = reinterpret_cast<unsigned short*>(st_slots + KP);             // MODE 0
     const int first = MODE == 0 ? 0 : (own_start + 1) >> 1;
     const int last = MODE == 0 ? own_count : (own_start + own_count) >> 1;
     for (int it = first + warp; it < last; it += TX_THREADS / 32) {
         const int sa = MODE == 0 ? own_start + it : 2 * it;
-        uint32_t word[TB_MAX_WORDS / 32];
-        int start[TB_MAX_WORDS / 32];
         int cnt = 0;
 #pragma unroll
         for (int q = 0; q < TB_MAX_WORDS / 32; q++) {
-            const int w = q * 32 + lane;
-            word[q] = 0u; start[q] = 0;
             if (q * 32 < Wc) {                                            // uniform
+                const int w = q * 32 + lane;
+                uint32_t v = 0u;
                 if (w < Wc) {
-                    word[q] = bits[(size_t)sa * W + w];
-                    if (MODE == 1) word[q] |= bits[(size_t)(sa + 1) * W + w];
+                    v = bits[(size_t)sa * W + w];
+                    if (MODE == 1) v |= bits[(size_t)(sa + 1) * W + w];
                 }
-                const int c = __popc(word[q]);
+                const int c = __popc(v);
                 int incl = c;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-                start[q] = cnt + incl - c;
+                for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += x; }
+                const int p0 = cnt + incl - c;
                 cnt += __shfl_sync(0xffffffffu, incl, 31);
+                if (w < Wc && cnt <= cap) {
+                    const int p1 = p0 + __popc(v & 0xffu), p2 = p1 + __popc(v & 0xff00u), p3 = p2 + __popc(v & 0xff0000u);
+                    s_wd[w] = v;
+                    *reinterpret_cast<uint2*>(s_pre + 4 * w) = make_uint2((uint32_t)p0 | ((uint32_t)p1 << 16), (uint32_t)p2 | ((uint32_t)p3 << 16));
+                    if (v & 0xffu) s_mk[p0] = 4 * w + 1;
+                    if (v & 0xff00u) s_mk[p1] = 4 * w + 2;
+                    if (v & 0xff0000u) s_mk[p2] = 4 * w + 3;
+                    if (v & 0xff000000u) s_mk[p3] = 4 * w + 4;
+                }
             }
         }
-        if (cnt > cap) continue;                                          // cannot happen: the host sizes KP from the largest list
-#pragma unroll
-        for (int q = 0; q < TB_MAX_WORDS / 32; q++) {
-            uint32_t m = word[q];
-            int e = start[q];
-            const int t0 = (q * 32 + lane) * 32;
-            while (m) {
-                const int t = t0 + __ffs((int)m) - 1;
-                m &= m - 1u;
-                st_slots[e] = map[t];
-                if (MODE == 0) st16[tile_list_pos(e)] = (unsigned short)(t * 16);
-                e++;
-            }
+        if (cnt > cap) {                                                  // cannot happen (the host sizes KP from the longest list); keep the markers clean
+            __syncwarp();
+            for (int e = lane; e < cap; e += 32) s_mk[e] = 0;
+            __syncwarp();
+            continue;
         }
         __syncwarp();
+        const unsigned long long ob = out_start[MODE == 0 ? sa : it];
+        unsigned short* l16 = nullptr;
+        unsigned short self16 = 0;
+        int e_end = cnt;
         if (MODE == 0) {
-            const int nb = (cnt + TILE_BLOCK - 1) / TILE_BLOCK;
-            const unsigned short self16 = (unsigned short)((own_pref + it) * 16);
-            for (int e = cnt + lane; e < nb * TILE_BLOCK; e += 32) st16[tile_list_pos(e)] = self16;      // x0_ij = 0: no contribution
-            __syncwarp();
             const unsigned long long b0 = blk_start[sa];
             if (lane == 0) t_off[sa] = (uint32_t)b0;
-            uint4* dst = reinterpret_cast<uint4*>(lists16 + b0 * TILE_BLOCK);
-            const uint4* src = reinterpret_cast<const uint4*>(st16);
-            for (int i = lane; i < nb * (TILE_BLOCK / 8); i += 32) dst[i] = src[i];
+            l16 = lists16 + b0 * TILE_BLOCK;
+            self16 = (unsigned short)((own_pref + it) * 16);              // pads behind the last entry: the particle itself (x0_ij = 0)
+            e_end = (cnt + TILE_BLOCK - 1) / TILE_BLOCK * TILE_BLOCK;
         }
-        const unsigned long long ob = out_start[MODE == 0 ? sa : it];
-        for (int e = lane; e < cnt; e += 32) out_slots[ob + e] = st_slots[e];
-        __syncwarp();
+        int carry = 0;
+        for (int e0 = 0; e0 < e_end; e0 += 32) {
+            const int e = e0 + lane;
+            int m = 0;
+            if (e < cnt) { m = s_mk[e]; s_mk[e] = 0; }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int x = __shfl_up_sync(0xffffffffu, m, o); if (lane >= o) m = max(m, x); }
+            m = max(m, carry);                                            // m - 1 = the byte entry e belongs to
+            carry = __shfl_sync(0xffffffffu, m, 31);
+            if (e < cnt) {
+                const int u = m - 1;
+                const uint32_t byte = (s_wd[u >> 2] >> ((u & 3) * 8)) & 0xffu;
+                const int t = u * 8 + lut[byte * 8 + (e - s_pre[u])];
+                out_slots[ob + e] = map[t];
+                if (MODE == 0) l16[tile_list_pos(e)] = (unsigned short)(t * 16);
+            } else if (MODE == 0) {
+                l16[tile_list_pos(e)] = self16;
+            }
+        }
+        __syncwarp();                                                     // s_wd / s_pre / s_mk are rewritten for the next item
     }
 }
 
@@ -282,7 +322,8 @@ __global__ void __launch_bounds__(256) k_tile_work(const int* __restrict__ tab, 
     if (k >= n_active) return;
     const int* row = tab + (size_t)k * TT_STRIDE;
     const unsigned long long pairs = nbr_start[row[TT_OWN_START] + row[TT_OWN_COUNT]] - nbr_start[row[TT_OWN_START]];
-    work_key[k] = 0x000fffffu - (uint32_t)(pairs < 0x000fffffull ? pairs : 0x000fffffull);      // ascending sort = descending work
+    const unsigned long long units = pairs >> 4;                                                // 16 bits (two radix passes) in units of 16 pairs
+    work_key[k] = 0x0000ffffu - (uint32_t)(units < 0x0000ffffull ? units : 0x0000ffffull);      // ascending sort = descending work
     work_val[k] = (uint32_t)k;
 }
 

@@ -580,9 +580,8 @@ extern "C" int mis_build_neighbors(MisSim* s, void* stream) {
         s->cell_dim[a] = hb[3 + a] - hb[a] + 1;
         if (s->cell_dim[a] > maxdim) maxdim = s->cell_dim[a];
     }
-    if (maxdim > 1024) return fail(MIS_E_UNSUPPORTED, "cell grid exceeds 1024 cells along an axis (30-bit Morton keys)");
     long long nc = (long long)s->cell_dim[0] * s->cell_dim[1] * s->cell_dim[2];
-    if (nc > (1ll << 28)) return fail(MIS_E_UNSUPPORTED, "dense cell table larger than 2^28 cells");
+    if (nc > (1ll << 28)) return fail(MIS_E_UNSUPPORTED, "dense cell table larger than 2^28 cells (the bounding box of x0 in cells of width 2h)");
     s->ncells = (int)nc;
     if (s->ncells > s->ncells_cap) {
         if (s->cell_start) cudaFree(s->cell_start);
@@ -598,11 +597,22 @@ extern "C" int mis_build_neighbors(MisSim* s, void* stream) {
     const int3 cdim = make_int3(s->cell_dim[0], s->cell_dim[1], s->cell_dim[2]);
     int bits = 1;
     while ((1 << bits) < maxdim) bits++;
+    // Up to 1024 cells per axis: the plain 3 x bits Morton code.  Wider scenes: a bit count per axis (morton3_axes); their sum is
+    // at most 31 because the dense table holds at most 2^28 cells.
+    int3 nbits = make_int3(bits, bits, bits);
+    int cell_bits = 3 * bits;
+    if (maxdim > 1024) {
+        int ab[3];
+        for (int a = 0; a < 3; a++) { ab[a] = 0; while ((1 << ab[a]) < s->cell_dim[a]) ab[a]++; }
+        nbits = make_int3(ab[0], ab[1], ab[2]);
+        cell_bits = ab[0] + ab[1] + ab[2];
+        if (cell_bits > 32) return fail(MIS_E_UNSUPPORTED, "cell grid needs more than 32 Morton key bits");
+    }
     // in-cell Morton refinement: as many of its 9 bits as fit a 32-bit key (multiples of 3)
-    s->sub_bits = 3 * bits + 9 <= 32 ? 9 : (3 * bits + 6 <= 32 ? 6 : (3 * bits + 3 <= 32 ? 3 : 0));
-    k_cell_keys<<<nblk(n, 256), 256, 0, st>>>(s->bcoords, s->subkey, n, cmin, s->sub_bits, s->keys);
+    s->sub_bits = cell_bits + 9 <= 32 ? 9 : (cell_bits + 6 <= 32 ? 6 : (cell_bits + 3 <= 32 ? 3 : 0));
+    k_cell_keys<<<nblk(n, 256), 256, 0, st>>>(s->bcoords, s->subkey, n, cmin, nbits, s->sub_bits, s->keys);
     CK_LAUNCH(); s->launches++;
-    s->launches += radix_sort_pairs(s->keys, s->perm, n, 3 * bits + s->sub_bits, s->rs, st);
+    s->launches += radix_sort_pairs(s->keys, s->perm, n, cell_bits + s->sub_bits, s->rs, st);
     CK_LAUNCH();
     k_cell_table<<<nblk(n, 256), 256, 0, st>>>(s->keys, s->perm, s->bcoords, s->x0_orig, n, cmin, cdim, s->sub_bits,
                                                s->cell_start, s->cell_end, s->cell_lin_sorted, s->inv_perm, s->x0m);

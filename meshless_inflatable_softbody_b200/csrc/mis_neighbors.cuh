@@ -77,13 +77,29 @@ __global__ void __launch_bounds__(256) k_cell_coords(const float* __restrict__ x
     }
 }
 
+// Morton code with its own bit count per axis: level b of an axis is present only while that axis still has bits (x below y below
+// z inside a level, as in morton3).  With equal counts this IS morton3; with unequal ones it is morton3 with the always-zero
+// bits of the short axes squeezed out -- the same order, fewer key bits: a scene fits 32 bits whenever its dense cell table
+// (<= 2^28 cells) exists, however elongated it is.
+__device__ __forceinline__ uint32_t morton3_axes(uint32_t x, uint32_t y, uint32_t z, int3 nbits) {
+    uint32_t key = 0u;
+    int pos = 0;
+    const int mb = max(nbits.x, max(nbits.y, nbits.z));
+    for (int b = 0; b < mb; b++) {
+        if (b < nbits.x) { key |= ((x >> b) & 1u) << pos; pos++; }
+        if (b < nbits.y) { key |= ((y >> b) & 1u) << pos; pos++; }
+        if (b < nbits.z) { key |= ((z >> b) & 1u) << pos; pos++; }
+    }
+    return key;
+}
 // key = Morton(cell - cmin) << sub_bits | top sub_bits bits of the 9-bit in-cell Morton code
 __global__ void __launch_bounds__(256) k_cell_keys(const int* __restrict__ coords, const uint32_t* __restrict__ subkey, int n, int3 cmin,
-                                                   int sub_bits, uint32_t* __restrict__ keys) {
+                                                   int3 nbits, int sub_bits, uint32_t* __restrict__ keys) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t cell = morton3((uint32_t)(coords[3 * i] - cmin.x), (uint32_t)(coords[3 * i + 1] - cmin.y), (uint32_t)(coords[3 * i + 2] - cmin.z));
-    keys[i] = (cell << sub_bits) | (subkey[i] >> (9 - sub_bits));
+    const uint32_t cx = (uint32_t)(coords[3 * i] - cmin.x), cy = (uint32_t)(coords[3 * i + 1] - cmin.y), cz = (uint32_t)(coords[3 * i + 2] - cmin.z);
+    const uint32_t cell = (nbits.x == nbits.y && nbits.y == nbits.z) ? morton3(cx, cy, cz) : morton3_axes(cx, cy, cz, nbits);
+    keys[i] = (cell << sub_bits) | (sub_bits ? subkey[i] >> (9 - sub_bits) : 0u);
 }
 
 // after the sort: dense cell table, inverse permutation, cell-sorted x0

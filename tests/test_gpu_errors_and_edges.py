@@ -46,10 +46,30 @@ def test_bad_arguments_are_rejected_with_a_message():
     assert L.mis_step(None, 1, None) == -1 and L.mis_destroy(None) == 0
 
 
-def test_scene_wider_than_the_key_range_is_unsupported_not_wrong():
-    # 1024 cells of width 2h along an axis is the limit of the 30-bit Morton key
-    x0 = np.array([[0.0, 0.07, 0.0], [1025 * 0.014, 0.07, 0.0]], np.float32)
-    with pytest.raises(native.MisError, match=r"\(-4\).*1024"):      # MIS_E_UNSUPPORTED
+def test_scene_wider_than_1024_cells_bins_with_per_axis_key_bits():
+    """Two bodies 1 500 cells (21 m) apart: more than the 1 024 cells per axis a 3 x 10-bit Morton key holds.  The key takes a bit
+    count per axis instead (11 + 4 + 4 here); lists and trajectory match the oracle as for any other scene."""
+    a, _ = scenes.jittered_sphere(400, seed=6, low_drop=True)
+    b = a.copy(); b[:, 0] += 1500 * 0.014
+    x0 = np.concatenate([a, b], 0).astype(np.float32)
+    sim, o, r = _sim(x0), make_oracle(x0), make_oracle(x0)
+    off, nb = (t.cpu().numpy() for t in sim.neighbors())
+    cnt, ooff, oflat = o.neighbor_lists()
+    assert np.array_equal(np.diff(off), cnt)
+    rows = np.repeat(np.arange(len(x0)), cnt)
+    assert np.array_equal(nb[np.lexsort((nb, rows))], oflat)
+    r.set_order(1)
+    sim.startup(); o.startup(); r.startup()
+    sim.step(50); o.step(50); r.step(50)
+    x, v = sim.position_velocity()
+    assert np.abs(x.cpu().numpy() - o.position()).max() <= 4 * np.abs(o.position() - r.position()).max() + 4e-9
+    assert np.abs(v.cpu().numpy() - o.velocity()).max() <= 4 * np.abs(o.velocity() - r.velocity()).max() + 2e-5
+
+
+def test_bounding_box_beyond_the_dense_cell_table_is_unsupported_not_wrong():
+    # 701^3 cells of width 2h > 2^28: the dense cell table is the limit
+    x0 = np.array([[0.0, 0.07, 0.0], [700 * 0.014, 0.07 + 700 * 0.014, 700 * 0.014]], np.float32)
+    with pytest.raises(native.MisError, match=r"\(-4\).*2\^28"):      # MIS_E_UNSUPPORTED
         _sim(x0)
 
 

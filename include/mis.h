@@ -169,6 +169,10 @@ int mis_export_slots(MisSim* sim, const int* ids_dev, int count, int* slots_dev,
  *                          locally), 2 = outer layer (only its position is used).  Clusters made of ghosts skip the force gather,
  *                          clusters made of outer-layer ghosts also the deformation gather (their owner does that work).
  *                          All ranks must have finished their set-up (host barrier) before the first step after connect.
+ *                          Epochs: every step and every re-prime (the first step after a setter / mis_set_state) publishes ONE
+ *                          epoch and waits for the same epoch of each peer, so all ranks of a partition must issue the same
+ *                          sequence of steps and state-changing calls (SPMD).  A rank that re-primes or steps alone runs ahead
+ *                          of its peers' flags: its next wait then returns on stale ghosts or times out (mis_halo_status).
  *   mis_halo_status      : synchronises `stream`; err = 1 if a flag wait timed out (MIS_HALO_TIMEOUT_MS, default 20 s).  */
 #define MIS_MAX_PEERS 4
 int mis_halo_ipc_handles(MisSim* sim, unsigned char* out192);
